@@ -1,0 +1,1389 @@
+/*
+ * flacb200_kernels.cuh -- device code of the B200 FLAC encode path.
+ *
+ * One CTA encodes one frame (all channels) from PCM in HBM to final bytes in HBM:
+ *
+ *   phase 0  frame/channel split: interleaved little-endian PCM -> int32 planes in shared
+ *            memory                                     (reference flac/encoder.py:87, :102)
+ *   phase 1  per channel: fixed-predictor errors, orders 0-4          (encoder.py:331-359)
+ *            windowed fp64 autocorrelation, Levinson-Durbin, coefficient quantisation,
+ *            integer residual error of every LPC order                (encoder.py:362-548)
+ *            fixed-vs-LPC choice                                      (encoder.py:135-157)
+ *            Rice partition search on the winner's residual           (encoder.py:632-760)
+ *            -> exact size of every subframe in bits
+ *   phase 2  frame size -> byte offset of the frame in the output stream by a decoupled
+ *            look-back over a device-wide array of frame sizes (single pass, no second
+ *            kernel, no compaction copy)
+ *   phase 3  frame header + CRC-8 (encoder.py:194-234), subframes (encoder.py:553-627),
+ *            Rice codes (encoder.py:765-806) packed MSB first (binary.py:144-216) in a shared
+ *            memory window, flushed to HBM; CRC-16 (encoder.py:159-165, crc.py)
+ *
+ * Work split inside the CTA: thread t of tile k owns the E consecutive samples
+ * [(k*B + t)*E, +E).  Consecutive samples per thread give the LPC kernels a register-resident
+ * history window and let each thread concatenate its own Rice codes in registers; only the
+ * first and last word of a thread's bit range are shared with a neighbour.
+ *
+ * The same source compiles for the CPU SIMT simulator of tests/sim (FLACB_CPU_SIM), which is
+ * test infrastructure: it lets the kernel logic be checked against the golden vectors on a
+ * machine without a GPU.
+ */
+#pragma once
+
+#include <stdint.h>
+
+#ifdef FLACB_CPU_SIM
+#include "cpu_sim.h"
+#else
+#include <cuda_runtime.h>
+#define FLACB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#include "../../include/flacb200.h"
+
+namespace flacb {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr int E = 8;            /* consecutive samples per thread per tile */
+constexpr int GUARD = 32;       /* zero history in front of every channel plane */
+constexpr int TAILPAD = 48;     /* zero samples behind a plane (window reads run past the end) */
+constexpr int STG_WORDS = 4096; /* staging window of the bit packer, 32-bit words */
+constexpr int MAXB = 576;       /* threads per CTA, upper bound */
+constexpr int MAX_CH = 8;
+constexpr int MAX_CAND = 16;    /* Rice partition orders 0..15 */
+constexpr int CRC_SLICE = 64;   /* bytes per thread in the parallel CRC-16 */
+constexpr int XPOW_HI = 8192;   /* x^(8*256*h) table entries: frames up to 2 MiB */
+constexpr unsigned FULL = 0xffffffffu;
+
+/* look-back state flags (top two bits of a 64-bit word, value below) */
+constexpr u64 LB_AGG = 1ull << 62;
+constexpr u64 LB_PREFIX = 2ull << 62;
+constexpr u64 LB_VALUE = (1ull << 62) - 1;
+
+/* plane index -> shared memory word: one pad word every 32 keeps the stride-E accesses of a
+ * warp on distinct banks */
+__host__ __device__ __forceinline__ uint32_t padidx(uint32_t i) { return i + (i >> 5); }
+
+struct EncParams {
+    const uint8_t *pcm;        /* interleaved, cbytes per sample, little endian */
+    u64 n_sample_frames;
+    int channels, bps, cbytes, block_size;
+    int L, P, rmin, rmax;
+    u64 first_frame_number;
+    uint32_t flags;
+    uint32_t n_frames;
+    int tail_size;             /* size of the last frame (== block_size when it is full) */
+    const double *win_full;    /* tukey(block_size), zero padded by 64 */
+    const double *win_tail;    /* tukey(tail_size), zero padded by 64 */
+    int win_full_bad, win_tail_bad; /* ZeroDivisionError of encoder.py:437 (n in 4..7) */
+    uint8_t *out;
+    u64 out_cap;
+    u64 slot_stride;           /* != 0: slot mode (frame f at f * slot_stride) */
+    uint32_t *frame_bytes;     /* [n_frames] */
+    u64 *frame_off;            /* [n_frames + 1] exclusive prefix (look-back mode) */
+    int32_t *frame_status;     /* [n_frames] */
+    u64 *lb_state;             /* [n_frames] look-back words, zeroed before launch */
+    uint32_t *ticket;          /* zeroed before launch */
+    u64 *stats;                /* device counters: [0..4] fixed order histogram, [5] lpc, [6] ood */
+    flacb_subframe_info *info; /* optional, device memory */
+    uint32_t smem_limit;
+};
+
+struct SmemLayout {
+    uint32_t xs, xwords, res, cum, kall, stg, fb, pst, red, total;
+    int xs_all;
+};
+
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+/* Shared memory plan for a block size / channel count.  xs_all = every channel plane resident;
+ * otherwise one plane that is (re)loaded per channel and phase. */
+__host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int rmax, uint32_t limit)
+{
+    SmemLayout l;
+    l.xwords = padidx((uint32_t)(GUARD + nmax + TAILPAD)) + 1;
+    uint32_t rest = 0;
+    uint32_t res_b = align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
+    uint32_t cum_b = align16(((uint32_t)nmax / E + 4) * 8);
+    uint32_t kall_b = align16(2u << rmax);
+    uint32_t stg_b = align16((STG_WORDS + 4) * 4);
+    uint32_t fb_b = align16(MAXB * 4);
+    uint32_t pst_b = align16((MAXB + 1) * 4);
+    uint32_t red_b = align16((MAXB / 32) * 32 * 8);
+    rest = res_b + cum_b + kall_b + stg_b + fb_b + pst_b + red_b;
+    uint32_t plane = align16(l.xwords * 4);
+    l.xs_all = ((u64)plane * (u64)channels + rest <= limit) ? 1 : 0;
+    uint32_t off = 0;
+    l.xs = off;
+    off += l.xs_all ? plane * (uint32_t)channels : plane;
+    l.res = off; off += res_b;
+    l.cum = off; off += cum_b;
+    l.kall = off; off += kall_b;
+    l.stg = off; off += stg_b;
+    l.fb = off; off += fb_b;
+    l.pst = off; off += pst_b;
+    l.red = off; off += red_b;
+    l.total = off;
+    return l;
+}
+
+#ifndef FLACB_HOST_ONLY
+
+/* CRC-16 helper tables: x^(8*l) mod P for l < 256 and x^(8*256*h) mod P (P = 0x18005) */
+__constant__ uint16_t c_xpow_lo[256];
+__constant__ uint16_t c_xpow_hi[XPOW_HI];
+__constant__ uint16_t c_crc16_tab[256];
+
+struct Decision {
+    int32_t type;   /* 0 fixed, 1 lpc */
+    int32_t order;  /* order field of the header */
+    int32_t warm;   /* warm-up samples == predictor order used by the Rice search */
+    int32_t shift, ncoef;
+    int32_t porder, method;
+    uint32_t bits;  /* serialised subframe size */
+    int32_t q[FLACB_MAX_LPC];
+};
+
+struct Shared {
+    double autoc[FLACB_MAX_LPC + 1];
+    double ldc[FLACB_MAX_LPC][FLACB_MAX_LPC]; /* Levinson coefficients after iteration k */
+    int32_t qc[FLACB_MAX_LPC][FLACB_MAX_LPC];
+    int32_t qshift[FLACB_MAX_LPC], qncoef[FLACB_MAX_LPC], qstat[FLACB_MAX_LPC];
+    uint32_t qabs[FLACB_MAX_LPC];
+    u64 lpc_err[FLACB_MAX_LPC];
+    u64 fixed_err[8];
+    u64 qsum[MAX_CAND];
+    Decision dec[MAX_CH];
+    uint32_t cand_o[MAX_CAND], cand_magic[MAX_CAND];
+    uint32_t sizeA[MAX_CAND], sizeB[MAX_CAND], any5[MAX_CAND];
+    uint32_t errkey;
+    int ncand;
+    int lev_stat;
+    /* packer */
+    uint32_t pos, wbase, crc;
+    u64 frame_off;
+    uint32_t frame_bytes, payload_bytes;
+    int status, writable, range_flag;
+    uint32_t frame;
+    uint32_t scan_warp[33];
+    u64 scan_warp64[33];
+    uint16_t crc16_tab[256];
+};
+
+struct Blk {
+    const EncParams &p;
+    Shared &sh;
+    int tid, B, lane, warp, nwarps;
+    int n;      /* block size of this frame */
+    int ntiles;
+    int32_t *xs;
+    uint32_t xwords;
+    uint32_t *res;
+    u64 *cum;
+    uint8_t *kall;
+    uint32_t *stg;
+    uint32_t *fb;
+    uint32_t *pst;
+    u64 *red;
+    const double *win;
+    __device__ Blk(const EncParams &p_, Shared &sh_) : p(p_), sh(sh_) {}
+};
+
+__device__ __forceinline__ void set_status(Blk &b, int code)
+{
+    /* first error in the reference's evaluation order wins; callers run in that order */
+    if (b.sh.status == 0) b.sh.status = code;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* block-wide primitives                                                                  */
+
+template <int K>
+__device__ void block_reduce_u64(Blk &b, u64 (&v)[K], u64 *out)
+{
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], off);
+    }
+    if (b.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) b.red[b.warp * K + k] = v[k];
+    }
+    __syncthreads();
+    if (b.tid < K) {
+        u64 s = 0;
+        for (int w = 0; w < b.nwarps; w++) s += b.red[w * K + b.tid];
+        out[b.tid] = s;
+    }
+    __syncthreads();
+}
+
+__device__ uint32_t block_excl_scan_u32(Blk &b, uint32_t v, uint32_t &total)
+{
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, off);
+        if (b.lane >= off) inc += t;
+    }
+    if (b.lane == 31) b.sh.scan_warp[b.warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int w = 0; w < b.nwarps; w++) {
+        uint32_t x = b.sh.scan_warp[w];
+        if (w < b.warp) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+__device__ u64 block_excl_scan_u64(Blk &b, u64 v, u64 &total)
+{
+    u64 inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        u64 t = __shfl_up_sync(FULL, inc, off);
+        if (b.lane >= off) inc += t;
+    }
+    if (b.lane == 31) b.sh.scan_warp64[b.warp] = inc;
+    __syncthreads();
+    u64 base = 0, tot = 0;
+    for (int w = 0; w < b.nwarps; w++) {
+        u64 x = b.sh.scan_warp64[w];
+        if (w < b.warp) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* phase 0: frame/channel split (encoder.py:87 batch, :102 de-interleave)                 */
+
+__device__ __forceinline__ int32_t load_sample(const uint8_t *base, u64 s, int cbytes, int bps,
+                                               bool aligned)
+{
+    int32_t v;
+    if (cbytes == 2) {
+        if (aligned) v = ((const int16_t *)base)[s];
+        else v = (int16_t)((uint32_t)base[2 * s] | ((uint32_t)base[2 * s + 1] << 8));
+    } else if (cbytes == 3) {
+        const uint8_t *q = base + 3 * s;
+        uint32_t u = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+        v = (int32_t)(u << 8) >> 8;
+    } else if (cbytes == 4) {
+        if (aligned) v = ((const int32_t *)base)[s];
+        else {
+            const uint8_t *q = base + 4 * s;
+            v = (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) |
+                          ((uint32_t)q[3] << 24));
+        }
+    } else {
+        v = (int8_t)base[s];
+    }
+    (void)bps;
+    return v;
+}
+
+/* c < 0: all channels into their planes (xs_all); otherwise channel c into plane 0 */
+__device__ void load_planes(Blk &b, int c_only)
+{
+    const EncParams &p = b.p;
+    const int ch = p.channels;
+    const uint8_t *base = p.pcm + (u64)b.sh.frame * (u64)p.block_size * (u64)ch * (u64)p.cbytes;
+    const bool aligned = (((uintptr_t)base) & (uintptr_t)(p.cbytes - 1)) == 0 || p.cbytes == 3 ||
+                         p.cbytes == 1;
+    const int planes = c_only < 0 ? ch : 1;
+    /* zero guard and tail pad */
+    for (int idx = b.tid; idx < planes * (GUARD + TAILPAD); idx += b.B) {
+        int pl = idx / (GUARD + TAILPAD);
+        int j = idx - pl * (GUARD + TAILPAD);
+        int i = j < GUARD ? j : b.n + j; /* logical index GUARD + n + (j - GUARD) */
+        b.xs[(uint32_t)pl * b.xwords + padidx((uint32_t)i)] = 0;
+    }
+    if (c_only < 0) {
+        const int total = b.n * ch;
+        if (ch == 1) {
+            for (int s = b.tid; s < total; s += b.B)
+                b.xs[padidx((uint32_t)(GUARD + s))] = load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
+        } else if (ch == 2) {
+            for (int s = b.tid; s < total; s += b.B)
+                b.xs[(uint32_t)(s & 1) * b.xwords + padidx((uint32_t)(GUARD + (s >> 1)))] =
+                    load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
+        } else {
+            for (int s = b.tid; s < total; s += b.B) {
+                int i = s / ch, c = s - i * ch;
+                b.xs[(uint32_t)c * b.xwords + padidx((uint32_t)(GUARD + i))] =
+                    load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
+            }
+        }
+    } else {
+        for (int i = b.tid; i < b.n; i += b.B)
+            b.xs[padidx((uint32_t)(GUARD + i))] =
+                load_sample(base, (u64)i * (u64)ch + (u64)c_only, p.cbytes, p.bps, aligned);
+    }
+    __syncthreads();
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:331-359 encode_subframe_fixed: sum |residual| of orders 0..4                */
+
+__device__ __forceinline__ void fixed_residuals(const int (&a)[E + 4], int e, int (&r)[5])
+{
+    const int x0 = a[e + 4], x1 = a[e + 3], x2 = a[e + 2], x3 = a[e + 1], x4 = a[e];
+    r[0] = x0;                                  /* common.py:15-21 coefficient table */
+    r[1] = x0 - x1;
+    r[2] = x0 - 2 * x1 + x2;
+    r[3] = x0 - 3 * x1 + 3 * x2 - x3;
+    r[4] = x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4;
+}
+
+__device__ void fixed_errors(Blk &b, const int32_t *x)
+{
+    u64 acc[5] = {0, 0, 0, 0, 0};
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int i0 = (tile * b.B + b.tid) * E;
+        if (i0 < b.n) {
+            int a[E + 4];
+#pragma unroll
+            for (int j = 0; j < E + 4; j++) a[j] = x[padidx((uint32_t)(GUARD + i0 - 4 + j))];
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int i = i0 + e;
+                if (i < b.n) {
+                    int r[5];
+                    fixed_residuals(a, e, r);
+#pragma unroll
+                    for (int o = 0; o < 5; o++)
+                        if (i >= o) acc[o] += (u64)(uint32_t)(r[o] < 0 ? -r[o] : r[o]);
+                }
+            }
+        }
+    }
+    block_reduce_u64<5>(b, acc, b.sh.fixed_err);
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:368-371, :443-450: windowed autocorrelation.  The reference sums with Python's
+ * builtin sum(), which is compensated (Neumaier) from 3.12 on and returns the correctly
+ * rounded exact sum on every lag we measured; a double-double accumulation in any order does
+ * the same.  Products and window multiplications are single IEEE operations (no FMA).       */
+
+__device__ __forceinline__ void dd_add(double &s, double &c, double x)
+{
+    const double t = __dadd_rn(s, x);
+    const double bb = __dsub_rn(t, s);
+    const double err = __dadd_rn(__dsub_rn(s, __dsub_rn(t, bb)), __dsub_rn(x, bb));
+    s = t;
+    c = __dadd_rn(c, err);
+}
+
+template <int LG>
+__device__ void autocorrelation(Blk &b, const int32_t *x, int L)
+{
+    const int n = b.n;
+    double2 *redd = (double2 *)b.red;
+    for (int lag0 = 0; lag0 <= L; lag0 += LG) {
+        double s[LG], c[LG];
+#pragma unroll
+        for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
+        for (int tile = 0; tile < b.ntiles; tile++) {
+            const int i0 = (tile * b.B + b.tid) * E;
+            if (i0 < n) {
+                double wa[E], wb[E + LG - 1];
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                    wa[e] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
+#pragma unroll
+                for (int j = 0; j < E + LG - 1; j++) {
+                    const int idx = i0 + lag0 + j;
+                    wb[j] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + idx))], b.win[idx]);
+                }
+#pragma unroll
+                for (int l = 0; l < LG; l++) {
+                    const int lag = lag0 + l;
+                    if (lag <= L) {
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            /* range(len - lag - 1): the last product is dropped (encoder.py:449) */
+                            if (i0 + e < n - lag - 1) dd_add(s[l], c[l], __dmul_rn(wa[e], wb[e + l]));
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < LG; l++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double s2 = __shfl_xor_sync(FULL, s[l], off);
+                const double c2 = __shfl_xor_sync(FULL, c[l], off);
+                dd_add(s[l], c[l], s2);
+                c[l] = __dadd_rn(c[l], c2);
+            }
+        }
+        if (b.lane == 0) {
+#pragma unroll
+            for (int l = 0; l < LG; l++) redd[b.warp * LG + l] = make_double2(s[l], c[l]);
+        }
+        __syncthreads();
+        if (b.tid < LG && lag0 + b.tid <= L) {
+            double S = 0.0, C = 0.0;
+            for (int w = 0; w < b.nwarps; w++) {
+                const double2 v = redd[w * LG + b.tid];
+                dd_add(S, C, v.x);
+                C = __dadd_rn(C, v.y);
+            }
+            b.sh.autoc[lag0 + b.tid] = __dadd_rn(S, C);
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:453-479 levinson_durbin, run once to the maximum order: the coefficient vector
+ * after iteration k equals levinson_durbin(autoc[:k+2]) bit for bit.  Strict IEEE operation
+ * order; `lambda ** 2` is evaluated as lambda*lambda (glibc pow differs by 1 ulp on ~0.08% of
+ * arguments; documented in DESIGN.md).  One thread.                                          */
+
+__device__ void levinson(Blk &b, int L)
+{
+    Shared &sh = b.sh;
+    double coefs[FLACB_MAX_LPC + 1];
+#pragma unroll 1
+    for (int i = 0; i <= L; i++) coefs[i] = 0.0;
+    coefs[0] = 1.0;
+    double error = sh.autoc[0];
+    int stat = 0;
+#pragma unroll 1
+    for (int k = 0; k < L; k++) {
+        double lambda = 0.0;
+#pragma unroll 1
+        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, __dmul_rn(coefs[j], sh.autoc[k + 1 - j]));
+        if (error == 0.0) { stat = FLACB_E_ZERODIV; break; }
+        lambda = __ddiv_rn(lambda, error);
+#pragma unroll 1
+        for (int m = 0; m <= (k + 1) / 2; m++) {
+            const double lo = coefs[m], hi = coefs[k + 1 - m];
+            const double temp = __dadd_rn(hi, __dmul_rn(lambda, lo));
+            coefs[m] = __dadd_rn(lo, __dmul_rn(lambda, hi));
+            coefs[k + 1 - m] = temp;
+        }
+        const double l2 = __dmul_rn(lambda, lambda);
+        if (isinf(l2) && !isinf(lambda)) { stat = FLACB_E_OVERFLOW; break; }
+        error = __dmul_rn(error, __dsub_rn(1.0, l2));
+#pragma unroll 1
+        for (int j = 0; j <= k; j++) sh.ldc[k][j] = coefs[j + 1];
+    }
+    sh.lev_stat = stat;
+}
+
+/* encoder.py:482-534 quantize_lpc_coefficients for order m (one thread per order) */
+__device__ void quantize_order(Blk &b, int m, int precision)
+{
+    Shared &sh = b.sh;
+    const double *c = sh.ldc[m - 1];
+    double cmax = 0.0;
+    bool any_nan = false;
+    for (int i = 0; i < m; i++) {
+        const double a = fabs(c[i]);
+        if (a != a) any_nan = true;
+        if (a > cmax) cmax = a;
+    }
+    sh.qncoef[m - 1] = 0;
+    sh.qshift[m - 1] = 0;
+    sh.qabs[m - 1] = 0;
+    sh.qstat[m - 1] = 0;
+    if (any_nan || !(cmax > 0.0)) { sh.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:496 */
+    if (isinf(cmax)) { sh.qstat[m - 1] = FLACB_E_OVERFLOW; return; }
+    int shift = precision - ilogb(cmax) - 2; /* floor(log2(cmax)) == exponent, encoder.py:503 */
+    if (shift > 15) shift = 15;
+    else if (shift < -16) { sh.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:508 */
+    if (shift < 0) return; /* encoder.py:523-532: loop never appends -> ([], 0) */
+    const i64 qmax = ((i64)1 << (precision - 1)) - 1;
+    const i64 qmin = -((i64)1 << (precision - 1));
+    const double scale = (double)((i64)1 << shift);
+    double error = 0.0;
+    uint32_t asum = 0;
+    for (int i = 0; i < m; i++) {
+        error = __dadd_rn(error, __dmul_rn(c[i], scale));
+        const double r = rint(error); /* round(): half to even */
+        const i64 qi = r < (double)qmin ? qmin : (r > (double)qmax ? qmax : (i64)r);
+        error = __dsub_rn(error, (double)qi);
+        sh.qc[m - 1][i] = (int32_t)qi;
+        asum += (uint32_t)(qi < 0 ? -qi : qi);
+    }
+    sh.qncoef[m - 1] = m;
+    sh.qshift[m - 1] = shift;
+    sh.qabs[m - 1] = asum;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:387-398: sum |residual| of every LPC order 1..L (prediction_residual,
+ * encoder.py:537-548).  History window in registers, coefficients broadcast from shared
+ * memory, 32-bit accumulation whenever sum|q| * 2^(bps-1) proves it exact.                 */
+
+template <int LMAX>
+__device__ void lpc_errors(Blk &b, const int32_t *x, int L)
+{
+    Shared &sh = b.sh;
+    const int n = b.n;
+    if (b.tid < FLACB_MAX_LPC) sh.lpc_err[b.tid] = 0;
+    __syncthreads();
+    const u64 lim32 = 1ull << 30;
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int i0 = (tile * b.B + b.tid) * E;
+        int h[LMAX + E];
+        if (i0 < n) {
+#pragma unroll
+            for (int j = 0; j < LMAX + E; j++) h[j] = x[padidx((uint32_t)(GUARD + i0 - LMAX + j))];
+        } else {
+#pragma unroll
+            for (int j = 0; j < LMAX + E; j++) h[j] = 0;
+        }
+#pragma unroll
+        for (int m = 1; m <= LMAX; m++) {
+            if (m <= L && sh.qncoef[m - 1] != 0) {
+                const int shift = sh.qshift[m - 1];
+                u64 tot = 0;
+                if (((u64)sh.qabs[m - 1] << (b.p.bps - 1)) <= lim32) {
+                    int acc[E];
+#pragma unroll
+                    for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+                    for (int j = 0; j < m; j++) {
+                        const int cj = sh.qc[m - 1][j];
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const int i = i0 + e;
+                        if (i >= m && i < n) {
+                            const int r = h[LMAX + e] - (acc[e] >> shift);
+                            tot += (u64)(uint32_t)(r < 0 ? -r : r);
+                        }
+                    }
+                } else {
+                    i64 acc[E];
+#pragma unroll
+                    for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+                    for (int j = 0; j < m; j++) {
+                        const i64 cj = sh.qc[m - 1][j];
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const int i = i0 + e;
+                        if (i >= m && i < n) {
+                            const i64 r = (i64)h[LMAX + e] - (acc[e] >> shift);
+                            tot += (u64)(r < 0 ? -r : r);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                if (b.lane == 0 && tot) atomicAdd(&sh.lpc_err[m - 1], tot);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* Winner's residual (encoder.py:537-548), zig-zag (utils.py:91-94) into res[], plus the
+ * running sum cum[g] = sum of res[0 .. g*E) that the Rice search reads partition sums from */
+
+template <int LMAX>
+__device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
+{
+    const int n = b.n;
+    u64 base = 0;
+    bool range_bad = false;
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int g = tile * b.B + b.tid;
+        const int i0 = g * E;
+        u64 run = 0;
+        if (i0 < n) {
+            uint32_t u[E];
+            if (d.type == 0) {
+                int a[E + 4];
+#pragma unroll
+                for (int j = 0; j < E + 4; j++) a[j] = x[padidx((uint32_t)(GUARD + i0 - 4 + j))];
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    int r[5];
+                    fixed_residuals(a, e, r);
+                    const int rr = d.order == 0 ? r[0] : d.order == 1 ? r[1] : d.order == 2 ? r[2]
+                                   : d.order == 3 ? r[3] : r[4];
+                    u[e] = ((uint32_t)rr << 1) ^ (uint32_t)(rr >> 31);
+                }
+            } else {
+                int h[LMAX + E];
+#pragma unroll
+                for (int j = 0; j < LMAX + E; j++) h[j] = x[padidx((uint32_t)(GUARD + i0 - LMAX + j))];
+                i64 acc[E];
+#pragma unroll
+                for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+                for (int j = 0; j < LMAX; j++) {
+                    if (j < d.ncoef) {
+                        const i64 cj = d.q[j];
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const i64 r = (i64)h[LMAX + e] - (acc[e] >> d.shift);
+                    const u64 z = ((u64)r << 1) ^ (u64)(r >> 63);
+                    if ((z >> 32) != 0 && i0 + e >= d.warm && i0 + e < n) range_bad = true;
+                    u[e] = (uint32_t)z;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int i = i0 + e;
+                if (i < d.warm || i >= n) u[e] = 0;
+                b.res[padidx((uint32_t)i)] = u[e];
+                run += u[e];
+            }
+        }
+        u64 total;
+        const u64 ex = block_excl_scan_u64(b, run, total);
+        if (i0 <= n + E) b.cum[g] = base + ex;
+        base += total;
+    }
+    if (range_bad) b.sh.range_flag = 1;
+    if (b.tid == 0) {
+        const int G = b.ntiles * b.B; /* run index just behind the last tile */
+        if (G * E <= n + E) b.cum[G] = base;
+    }
+    __syncthreads();
+    if (b.tid == 0 && b.sh.range_flag) set_status(b, FLACB_E_RANGE);
+    __syncthreads();
+}
+
+/* sum of res[0 .. pos) */
+__device__ __forceinline__ u64 cum_at(const Blk &b, int pos)
+{
+    const int g = pos / E;
+    u64 s = b.cum[g];
+    for (int j = g * E; j < pos; j++) s += b.res[padidx((uint32_t)j)];
+    return s;
+}
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t i, uint32_t d, uint32_t magic)
+{
+    return d == 1 ? i : __umulhi(i, magic); /* exact for i, d < 2^16; magic = ceil(2^32 / d) */
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:655-760 rice_partitions: every candidate order is evaluated, parameter
+ * k = floor(log2(sum / len)) per partition (find_rice_parameter), size estimate with the
+ * reference's per-partition "+4" (estimate_rice_partition_size_and_parameter), first minimum.
+ * Returns through d.porder / d.method and the exact number of residual bits in *res_bits.
+ * keep_params: leave kall[] valid for the chosen order (phase 3).                           */
+
+__device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
+{
+    Shared &sh = b.sh;
+    const EncParams &p = b.p;
+    const int n = b.n;
+    if (b.tid == 0) {
+        int nc = 0;
+        for (int o = p.rmin; o <= p.rmax; o++) { /* encoder.py:664-667 */
+            if ((n % (1 << o)) == 0 && (n >> o) > d.warm) {
+                sh.cand_o[nc] = (uint32_t)o;
+                const uint32_t psz = (uint32_t)(n >> o);
+                sh.cand_magic[nc] = psz == 1 ? 0u : 0xFFFFFFFFu / psz + 1u;
+                nc++;
+            }
+        }
+        if (nc == 0) {
+            /* encoder.py:669 assert: no admissible partition order.  Status recorded; the
+             * frame is still laid out with order 0 so that the stream stays well formed. */
+            set_status(b, FLACB_E_ASSERT);
+            sh.cand_o[0] = 0;
+            sh.cand_magic[0] = n == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)n + 1u;
+            nc = 1;
+        }
+        sh.ncand = nc;
+        sh.errkey = 0xFFFFFFFFu;
+    }
+    if (b.tid < MAX_CAND) sh.sizeA[b.tid] = 0, sh.sizeB[b.tid] = 0, sh.any5[b.tid] = 0, sh.qsum[b.tid] = 0;
+    __syncthreads();
+    const int ncand = sh.ncand;
+    /* parameters of every (order, partition) */
+    for (int ci = 0; ci < ncand; ci++) {
+        const int o = (int)sh.cand_o[ci];
+        const int psz = n >> o;
+        uint32_t a_loc = 0, b_loc = 0, f5 = 0;
+        for (int pi = b.tid; pi < (1 << o); pi += b.B) {
+            const int start = pi * psz < d.warm ? d.warm : pi * psz;
+            const int end = (pi + 1) * psz;
+            const uint32_t len = (uint32_t)(end - start);
+            const u64 sum = cum_at(b, end) - cum_at(b, start);
+            int k;
+            if (sum < (u64)len) {
+                /* mean < 1: math domain error (sum == 0, encoder.py:753) or a negative shift
+                 * count (encoder.py:758).  Lenient policy: parameter 0. */
+                atomicMin(&sh.errkey, ((uint32_t)ci << 20) | ((uint32_t)pi << 4) | FLACB_E_VALUE);
+                k = 0;
+            } else {
+                k = (63 - __clzll(sum)) - (31 - __clz(len));
+                if (((u64)len << k) > sum) k--;
+            }
+            b.kall[(1u << o) + (uint32_t)pi] = (uint8_t)k;
+            a_loc += 4u + (k > 14 ? 5u : 4u); /* encoder.py:718-725 */
+            b_loc += len * (uint32_t)(1 + k);
+            if (k > 14) f5 = 1;
+        }
+        if (a_loc) {
+            atomicAdd(&sh.sizeA[ci], a_loc);
+            atomicAdd(&sh.sizeB[ci], b_loc);
+            if (f5) atomicOr(&sh.any5[ci], 1u);
+        }
+    }
+    __syncthreads();
+    /* sum over samples of (u >> k) for every candidate order (rice_size, encoder.py:756-760) */
+    u64 acc[MAX_CAND];
+#pragma unroll
+    for (int ci = 0; ci < MAX_CAND; ci++) acc[ci] = 0;
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int i0 = (tile * b.B + b.tid) * E;
+        if (i0 < n) {
+            uint32_t u[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) u[e] = b.res[padidx((uint32_t)(i0 + e))];
+#pragma unroll
+            for (int ci = 0; ci < MAX_CAND; ci++) {
+                if (ci < ncand) {
+                    const uint32_t o = sh.cand_o[ci];
+                    const uint32_t psz = (uint32_t)n >> o;
+                    const uint32_t magic = sh.cand_magic[ci];
+                    const uint8_t *kk = b.kall + (1u << o);
+                    if (psz >= (uint32_t)E) {
+                        const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
+                        const uint32_t bnd = (p0 + 1) * psz;
+                        const uint32_t k0 = kk[p0];
+                        const uint32_t k1 = (p0 + 1 < (1u << o)) ? kk[p0 + 1] : 0u;
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[ci] += u[e] >> ((uint32_t)(i0 + e) < bnd ? k0 : k1);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            if (i0 + e < n) acc[ci] += u[e] >> kk[fast_div((uint32_t)(i0 + e), psz, magic)];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    block_reduce_u64<MAX_CAND>(b, acc, sh.qsum);
+    if (b.tid == 0) {
+        int best = 0;
+        u64 best_size = 0;
+        for (int ci = 0; ci < ncand; ci++) { /* first minimum, encoder.py:685-695 */
+            const u64 size = (u64)sh.sizeA[ci] + (u64)sh.sizeB[ci] + sh.qsum[ci];
+            if (ci == 0 || size < best_size) best = ci, best_size = size;
+        }
+        d.porder = (int)sh.cand_o[best];
+        d.method = sh.any5[best] ? 5 : 4; /* encoder.py:648-650 */
+        /* method (2) + partition order (4) + one parameter per partition + the codes */
+        sh.sizeA[0] = 6u + ((uint32_t)d.method << d.porder) + sh.sizeB[best] + (uint32_t)sh.qsum[best];
+        if (sh.errkey != 0xFFFFFFFFu) set_status(b, (int)(sh.errkey & 15u));
+    }
+    __syncthreads();
+    *res_bits = sh.sizeA[0];
+    __syncthreads();
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* bit packer (binary.py:144-216 Put: MSB first)                                          */
+
+/* serial put by one thread into the staging window */
+__device__ __forceinline__ void put_serial(Blk &b, uint32_t v, int nb)
+{
+    Shared &sh = b.sh;
+    const uint32_t off = sh.pos & 31u;
+    const uint32_t w = (sh.pos >> 5) - sh.wbase;
+    const u64 xx = (u64)v << (64 - (int)off - nb);
+    b.stg[w] |= (uint32_t)(xx >> 32);
+    if ((uint32_t)xx) b.stg[w + 1] |= (uint32_t)xx;
+    sh.pos += (uint32_t)nb;
+}
+
+__device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t bb)
+{
+    uint32_t r = 0; /* polynomial product modulo 0x18005 (common.py:13) */
+#pragma unroll
+    for (int i = 15; i >= 0; i--) {
+        r <<= 1;
+        if (r & 0x10000u) r ^= 0x18005u;
+        if ((bb >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+/* Flush the first `nbytes` bytes of the staging window to the frame in HBM and fold them into
+ * the frame CRC-16 (crc.py:25-30): every thread takes a 64-byte slice, and because the CRC has
+ * zero init and no final xor, crc(A || B) = crc(A) * x^(8|B|) + crc(B), so a slice's CRC times
+ * x^(8 * bytes behind it) can simply be xor-ed into the frame's.  Then the window is rebased at
+ * word `wend` (the partial word, if any, moves to the front). */
+__device__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
+{
+    Shared &sh = b.sh;
+    const uint32_t byte0 = sh.wbase * 4u; /* frame-relative */
+    if (sh.writable) {
+        uint8_t *dst = b.p.out + sh.frame_off + byte0;
+        for (uint32_t idx = (uint32_t)b.tid; idx < nbytes; idx += (uint32_t)b.B)
+            dst[idx] = (uint8_t)(b.stg[idx >> 2] >> (24u - 8u * (idx & 3u)));
+    }
+    const uint32_t nslices = (nbytes + CRC_SLICE - 1) / CRC_SLICE;
+    for (uint32_t sl = (uint32_t)b.tid; sl < nslices; sl += (uint32_t)b.B) {
+        const uint32_t lo = sl * CRC_SLICE;
+        const uint32_t hi = lo + CRC_SLICE < nbytes ? lo + CRC_SLICE : nbytes;
+        uint32_t c = 0;
+        for (uint32_t idx = lo; idx < hi; idx++) {
+            const uint32_t byte = (b.stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
+            c = ((c << 8) ^ sh.crc16_tab[(c >> 8) ^ byte]) & 0xFFFFu;
+        }
+        const uint32_t behind = sh.payload_bytes - (byte0 + hi);
+        const uint32_t w = gf16_mul(c_xpow_lo[behind & 255u], c_xpow_hi[behind >> 8]);
+        atomicXor(&sh.crc, gf16_mul(c, w));
+    }
+    const uint32_t carry_idx = wend - sh.wbase;
+    const uint32_t carry = carry_idx <= STG_WORDS ? b.stg[carry_idx] : 0u;
+    __syncthreads();
+    for (int idx = b.tid; idx < STG_WORDS + 4; idx += b.B) b.stg[idx] = idx == 0 ? carry : 0u;
+    if (b.tid == 0) sh.wbase = wend;
+    __syncthreads();
+}
+
+/* thread-local concatenation of this thread's fields; see pack_residual */
+struct Packer {
+    u64 acc;
+    uint32_t w;       /* word the high half of acc belongs to */
+    uint32_t f_w, l_w;
+    uint32_t win_lo, win_hi;
+    uint32_t firstv, lastv;
+    bool own_first, rmw_first;
+    uint32_t *stg;
+
+    __device__ __forceinline__ void out_word(uint32_t wi, uint32_t v)
+    {
+        if (wi == f_w && !own_first) firstv = v;
+        else if (wi == l_w) lastv = v;
+        else if (wi >= win_lo && wi < win_hi) {
+            if (wi == f_w && rmw_first) stg[wi - win_lo] |= v;
+            else stg[wi - win_lo] = v;
+        }
+    }
+    __device__ __forceinline__ void put(uint32_t bp, uint32_t v, int nb)
+    {
+        const uint32_t tw = bp >> 5;
+        if (tw != w) {
+            out_word(w, (uint32_t)(acc >> 32));
+            if (tw == w + 1) acc <<= 32;
+            else {
+                const uint32_t lo = (uint32_t)acc;
+                if (lo) out_word(w + 1, lo);
+                acc = 0;
+            }
+            w = tw;
+        }
+        acc |= (u64)v << (64 - (int)(bp & 31u) - nb);
+    }
+    __device__ __forceinline__ void finish(uint32_t p_end)
+    {
+        out_word(w, (uint32_t)(acc >> 32));
+        if (((p_end - 1u) >> 5) > w) out_word(w + 1, (uint32_t)acc);
+    }
+};
+
+/* encoder.py:765-806 put_residual: method, partition order, then per partition the parameter
+ * and one Rice code per sample (u >> k zeros, a one, k low bits).  Every thread packs the codes
+ * of its E consecutive samples into registers; the words strictly inside its bit range are
+ * plain shared-memory stores, the first word (shared with the previous thread) is handed to the
+ * thread that owns it, and each owner ors the pieces of its last word together.  No atomics. */
+__device__ void pack_residual(Blk &b, const Decision &d)
+{
+    Shared &sh = b.sh;
+    const int n = b.n;
+    const uint32_t psz = (uint32_t)n >> d.porder;
+    const uint32_t magic = psz == 1 ? 0u : 0xFFFFFFFFu / psz + 1u;
+    const uint8_t *kk = b.kall + (1u << d.porder);
+    const uint32_t method_code = d.method == 4 ? 0u : 1u;
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int i0 = (tile * b.B + b.tid) * E;
+        uint32_t u[E], k[E], pre[E]; /* pre: number of prefix bits in front of the code */
+        uint32_t nbits = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int i = i0 + e;
+            u[e] = 0, k[e] = 0, pre[e] = 0;
+            if (i >= d.warm && i < n) {
+                const uint32_t pi = fast_div((uint32_t)i, psz, magic);
+                const uint32_t pstart = pi * psz < (uint32_t)d.warm ? (uint32_t)d.warm : pi * psz;
+                u[e] = b.res[padidx((uint32_t)i)];
+                k[e] = kk[pi];
+                if ((uint32_t)i == pstart) pre[e] = (uint32_t)d.method + (i == d.warm ? 6u : 0u);
+                nbits += pre[e] + (u[e] >> k[e]) + 1u + k[e];
+            }
+        }
+        uint32_t tile_bits;
+        const uint32_t ex = block_excl_scan_u32(b, nbits, tile_bits);
+        b.pst[b.tid] = sh.pos + ex;
+        if (tile_bits == 0) continue; /* uniform */
+        const uint32_t tile_end = sh.pos + tile_bits;
+        if ((tile_end >> 5) >= sh.wbase + STG_WORDS) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
+        else __syncthreads();
+        const uint32_t p_start = sh.pos + ex;
+        const uint32_t p_end = p_start + nbits;
+        for (;;) {
+            Packer pk;
+            pk.stg = b.stg;
+            pk.win_lo = sh.wbase;
+            pk.win_hi = sh.wbase + STG_WORDS;
+            pk.acc = 0;
+            pk.w = p_start >> 5;
+            pk.f_w = p_start >> 5;
+            pk.l_w = nbits ? (p_end - 1u) >> 5 : pk.f_w;
+            pk.rmw_first = b.tid == 0;
+            pk.own_first = b.tid == 0 || (nbits != 0 && (p_start & 31u) == 0);
+            pk.firstv = 0;
+            pk.lastv = 0;
+            if (nbits) {
+                uint32_t cur = p_start;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int i = i0 + e;
+                    if (i >= d.warm && i < n) {
+                        if (pre[e]) {
+                            if (pre[e] > (uint32_t)d.method) {
+                                pk.put(cur, (method_code << 4) | (uint32_t)d.porder, 6); /* encoder.py:766-767 */
+                                cur += 6;
+                            }
+                            pk.put(cur, k[e], d.method); /* encoder.py:791 */
+                            cur += (uint32_t)d.method;
+                        }
+                        const uint32_t q = u[e] >> k[e];
+                        cur += q; /* q zeros: the window is pre-zeroed (encoder.py:802) */
+                        pk.put(cur, (1u << k[e]) | (u[e] & ((1u << k[e]) - 1u)), (int)k[e] + 1);
+                        cur += k[e] + 1u;
+                    }
+                }
+                pk.finish(p_end);
+            }
+            b.fb[b.tid] = pk.firstv;
+            __syncthreads();
+            /* thread 0 also owns the word the tile starts in when earlier bits sit in it */
+            const bool owns_last = (nbits != 0 || (b.tid == 0 && (p_start & 31u) != 0)) &&
+                                   !(pk.l_w == pk.f_w && !pk.own_first);
+            if (owns_last && pk.l_w >= pk.win_lo && pk.l_w < pk.win_hi) {
+                uint32_t v = pk.lastv;
+                for (int t = b.tid + 1; t < b.B && (b.pst[t] >> 5) == pk.l_w; t++) v |= b.fb[t];
+                if (b.tid == 0 && pk.l_w == pk.f_w) b.stg[pk.l_w - pk.win_lo] |= v;
+                else b.stg[pk.l_w - pk.win_lo] = v;
+            }
+            __syncthreads();
+            if ((tile_end >> 5) < sh.wbase + STG_WORDS) break;
+            flush_window(b, STG_WORDS * 4u, sh.wbase + STG_WORDS);
+        }
+        if (b.tid == 0) sh.pos = tile_end;
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* encoder.py:194-234 put_frame_header (+ coded_number.py:7-39, crc.py:17-22)              */
+
+__device__ int build_frame_header(const EncParams &p, int bs, u64 number, uint8_t *h)
+{
+    int code = 0, extra = 0;
+    switch (bs) { /* common.py:85-105 */
+    case 192: code = 1; break;
+    case 576: code = 2; break;
+    case 1152: code = 3; break;
+    case 2304: code = 4; break;
+    case 4608: code = 5; break;
+    case 256: code = 8; break;
+    case 512: code = 9; break;
+    case 1024: code = 10; break;
+    case 2048: code = 11; break;
+    case 4096: code = 12; break;
+    case 8192: code = 13; break;
+    case 16384: code = 14; break;
+    case 32768: code = 15; break;
+    default:
+        if (bs <= 255) code = 6, extra = 8; /* encoder.py:245-255 */
+        else code = 7, extra = 16;
+    }
+    int len = 0;
+    h[len++] = 0xFF; /* sync 0x7FFC (15 bits) + blocking strategy 0 */
+    h[len++] = 0xF8;
+    h[len++] = (uint8_t)(code << 4); /* sample rate 0000: from STREAMINFO (encoder.py:94) */
+    const uint32_t chn = (p.flags & FLACB_SPEC_CHANNELS) ? (uint32_t)(p.channels - 1) : 1u; /* encoder.py:95 */
+    h[len++] = (uint8_t)(chn << 4); /* sample size 000 + reserved 0 (encoder.py:96) */
+    const int nb = 64 - __clzll(number | 1ull) - ((number == 0) ? 1 : 0);
+    if (nb <= 7) h[len++] = (uint8_t)number;
+    else {
+        const int size = nb <= 11 ? 2 : nb <= 16 ? 3 : nb <= 21 ? 4 : nb <= 26 ? 5 : 6;
+        for (int i = 0; i < size; i++) {
+            const uint8_t six = (uint8_t)((number >> (6 * (size - 1 - i))) & 0x3F);
+            h[len++] = i == 0 ? (uint8_t)((((1u << size) - 1u) << (8 - size)) | six) : (uint8_t)(0x80 | six);
+        }
+    }
+    if (extra == 8) h[len++] = (uint8_t)(bs - 1);
+    else if (extra == 16) h[len++] = (uint8_t)((bs - 1) >> 8), h[len++] = (uint8_t)(bs - 1);
+    uint32_t crc = 0; /* crc.py:17-22, polynomial 0x107 */
+    for (int i = 0; i < len; i++) {
+        crc ^= h[i];
+        for (int bit = 0; bit < 8; bit++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xFFu : (crc << 1) & 0xFFu;
+    }
+    h[len++] = (uint8_t)crc;
+    return len;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* the kernel                                                                             */
+
+template <int LMAX>
+__device__ void analyse_channel(Blk &b, const int32_t *x, int c)
+{
+    Shared &sh = b.sh;
+    const EncParams &p = b.p;
+    const int n = b.n;
+    const int L = p.L;
+    Decision &d = sh.dec[c];
+    flacb_subframe_info *inf = p.info ? p.info + ((u64)sh.frame * (u64)p.channels + (u64)c) : nullptr;
+
+    fixed_errors(b, x);
+    bool lpc_ok = false;
+    if (L > 0) {
+        const int bad_win = (sh.frame == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail_bad : p.win_full_bad;
+        if (bad_win) {
+            if (b.tid == 0) set_status(b, FLACB_E_ZERODIV); /* encoder.py:437 */
+        } else {
+            autocorrelation<4>(b, x, L);
+            if (b.tid == 0) levinson(b, L);
+            __syncthreads();
+            if (sh.lev_stat == 0) {
+                if (b.tid < L) quantize_order(b, b.tid + 1, p.P);
+                __syncthreads();
+                if (b.tid == 0) {
+                    int st = 0;
+                    for (int m = 0; m < L && st == 0; m++) st = sh.qstat[m];
+                    sh.lev_stat = st;
+                }
+                __syncthreads();
+            }
+            if (sh.lev_stat == 0) {
+                lpc_errors<LMAX>(b, x, L);
+                lpc_ok = true;
+            } else if (b.tid == 0) set_status(b, sh.lev_stat);
+        }
+        __syncthreads();
+    }
+    if (b.tid == 0) {
+        /* encoder.py:352 first minimum over the fixed orders (order 0 only when n <= 4) */
+        int fo = 0;
+        if (n > 4)
+            for (int o = 1; o < 5; o++)
+                if (sh.fixed_err[o] < sh.fixed_err[fo]) fo = o;
+        const u64 ftotal = sh.fixed_err[fo];
+        int lo = 0;
+        u64 ltotal = 0;
+        if (lpc_ok) {
+            for (int m = 1; m <= L; m++) { /* encoder.py:404 first minimum */
+                /* negative-shift quirk: no coefficients -> residual is the signal itself */
+                const u64 t = sh.qncoef[m - 1] ? sh.lpc_err[m - 1] : sh.fixed_err[0];
+                if (m == 1 || t < ltotal) lo = m, ltotal = t;
+            }
+        }
+        bool use_lpc = false;
+        if (lpc_ok) { /* encoder.py:135-157 */
+            if (ltotal < ftotal) use_lpc = true;
+            else if (!(ftotal < ltotal)) set_status(b, FLACB_E_ASSERT);
+        }
+        if (use_lpc && (lo >= n || sh.qncoef[lo - 1] == 0)) {
+            /* only reachable on tails not longer than the order: the reference then fails in
+             * rice_partitions (encoder.py:669) */
+            set_status(b, FLACB_E_ASSERT);
+            use_lpc = false;
+        }
+        d.type = use_lpc ? 1 : 0;
+        d.order = use_lpc ? lo : fo;
+        d.warm = d.order;
+        d.shift = use_lpc ? sh.qshift[lo - 1] : 0;
+        d.ncoef = use_lpc ? lo : 0;
+        if (use_lpc)
+            for (int j = 0; j < lo; j++) d.q[j] = sh.qc[lo - 1][j];
+        if (use_lpc && p.P - 1 == 15) set_status(b, FLACB_E_ASSERT); /* encoder.py:619 */
+        if (inf) {
+            inf->type = d.type;
+            inf->order = d.order;
+            inf->shift = d.shift;
+            inf->precision = use_lpc ? p.P : 0;
+            inf->fixed_order = fo;
+            inf->lpc_order = lpc_ok ? lo : 0;
+            for (int o = 0; o < 5; o++) inf->fixed_err[o] = (n <= 4 && o > 0) ? -1 : (int64_t)sh.fixed_err[o];
+            for (int m = 0; m < FLACB_MAX_LPC; m++) {
+                const bool have = lpc_ok && m < L;
+                inf->lpc_err[m] = have ? (int64_t)(sh.qncoef[m] ? sh.lpc_err[m] : sh.fixed_err[0]) : 0;
+                inf->lpc_shift[m] = have ? sh.qshift[m] : 0;
+                inf->lpc_ncoef[m] = have ? sh.qncoef[m] : 0;
+                for (int j = 0; j < FLACB_MAX_LPC; j++) inf->lpc_q[m][j] = (have && j < sh.qncoef[m]) ? sh.qc[m][j] : 0;
+            }
+            for (int l = 0; l <= FLACB_MAX_LPC; l++) inf->autoc[l] = (L > 0 && l <= L) ? sh.autoc[l] : 0.0;
+        }
+    }
+    __syncthreads();
+    residual_and_cum<LMAX>(b, x, d);
+    uint32_t res_bits;
+    rice_search(b, d, &res_bits);
+    if (b.tid == 0) {
+        /* encoder.py:553-627: header byte, warm-up, [precision, shift, coefficients], residual */
+        uint32_t bits = 8u + (uint32_t)d.warm * (uint32_t)p.bps + res_bits;
+        if (d.type == 1) bits += 4u + 5u + (uint32_t)d.ncoef * (uint32_t)p.P;
+        d.bits = bits;
+        if (inf) {
+            inf->porder = d.porder;
+            inf->method = d.method;
+            inf->bits = bits;
+            inf->nparams = 1 << d.porder;
+            for (int i = 0; i < FLACB_INFO_PARAMS; i++) inf->params[i] = i < (1 << d.porder) ? b.kall[(1u << d.porder) + i] : 0;
+        }
+    }
+    __syncthreads();
+}
+
+template <int LMAX>
+__global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams p)
+{
+    FLACB_DYN_SMEM(smem);
+    __shared__ Shared sh;
+    Blk b(p, sh);
+    b.tid = (int)threadIdx.x;
+    b.B = (int)blockDim.x;
+    b.lane = b.tid & 31;
+    b.warp = b.tid >> 5;
+    b.nwarps = b.B >> 5;
+
+    if (b.tid == 0) {
+        /* frames are taken in launch order so that every predecessor of a frame is already
+         * running (or done) when the frame looks back for its offset */
+        sh.frame = p.slot_stride ? blockIdx.x : atomicAdd(p.ticket, 1u);
+        sh.status = 0;
+        sh.range_flag = 0;
+        sh.crc = 0;
+        sh.pos = 0;
+        sh.wbase = 0;
+    }
+    for (int i = b.tid; i < 256; i += b.B) sh.crc16_tab[i] = c_crc16_tab[i];
+    __syncthreads();
+    const uint32_t f = sh.frame;
+    b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
+    b.ntiles = (b.n + b.B * E - 1) / (b.B * E);
+    b.win = (f == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail : p.win_full;
+
+    const SmemLayout lay = make_layout(p.block_size, p.channels, p.rmax, p.smem_limit);
+    b.xs = (int32_t *)(smem + lay.xs);
+    b.xwords = lay.xwords;
+    b.res = (uint32_t *)(smem + lay.res);
+    b.cum = (u64 *)(smem + lay.cum);
+    b.kall = (uint8_t *)(smem + lay.kall);
+    b.stg = (uint32_t *)(smem + lay.stg);
+    b.fb = (uint32_t *)(smem + lay.fb);
+    b.pst = (uint32_t *)(smem + lay.pst);
+    b.red = (u64 *)(smem + lay.red);
+
+    /* ---- phase 0 + 1 ---- */
+    if (lay.xs_all) load_planes(b, -1);
+    for (int c = 0; c < p.channels; c++) {
+        if (!lay.xs_all) load_planes(b, c);
+        analyse_channel<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+    }
+
+    /* ---- phase 2: frame size -> offset ---- */
+    __shared__ uint8_t hdr[16];
+    __shared__ int hdr_len;
+    if (b.tid == 0) {
+        hdr_len = build_frame_header(p, b.n, p.first_frame_number + f, hdr);
+        u64 bits = (u64)hdr_len * 8u;
+        for (int c = 0; c < p.channels; c++) bits += sh.dec[c].bits;
+        sh.payload_bytes = (uint32_t)((bits + 7) >> 3); /* encoder.py:159-160 zero padding */
+        sh.frame_bytes = sh.payload_bytes + 2u;        /* + CRC-16 */
+        p.frame_bytes[f] = sh.frame_bytes;
+    }
+    __syncthreads();
+    if (p.slot_stride) {
+        if (b.tid == 0) sh.frame_off = (u64)f * p.slot_stride;
+    } else if (b.warp == 0) {
+        /* decoupled look-back, one warp: 32 predecessors per probe */
+        const u64 mine = (u64)sh.frame_bytes;
+        u64 excl = 0;
+        bool failed = false;
+        if (f > 0) {
+            if (b.lane == 0) atomicExch(&p.lb_state[f], LB_AGG | mine);
+            int64_t j = (int64_t)f - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const int64_t idx = j - b.lane;
+                u64 s = LB_PREFIX; /* before frame 0: an empty prefix */
+                if (idx >= 0) s = *(volatile u64 *)&p.lb_state[idx];
+                const uint32_t flag = (uint32_t)(s >> 62);
+                const unsigned has_prefix = __ballot_sync(FULL, flag == 2);
+                const unsigned invalid = __ballot_sync(FULL, flag == 0);
+                const int first_prefix = has_prefix ? __ffs((int)has_prefix) - 1 : 32;
+                const unsigned need = first_prefix == 32 ? FULL : ((2u << first_prefix) - 1u);
+                if (invalid & need) { /* a predecessor has not published yet */
+                    if (++spins > (1u << 22)) { failed = true; break; }
+                    __nanosleep(64);
+                    continue;
+                }
+                u64 v = (b.lane <= first_prefix) ? (s & LB_VALUE) : 0ull;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+                excl += v;
+                if (first_prefix < 32) break;
+                j -= 32;
+            }
+        }
+        if (b.lane == 0) {
+            atomicExch(&p.lb_state[f], LB_PREFIX | ((excl + mine) & LB_VALUE));
+            sh.frame_off = excl;
+            p.frame_off[f] = excl;
+            if (f == p.n_frames - 1) p.frame_off[p.n_frames] = excl + mine;
+            if (failed) set_status(b, FLACB_E_INTERNAL);
+        }
+    }
+    __syncthreads();
+    if (b.tid == 0) {
+        const u64 lim = p.slot_stride ? p.slot_stride : p.out_cap - (sh.frame_off < p.out_cap ? sh.frame_off : p.out_cap);
+        sh.writable = (u64)sh.frame_bytes <= lim && (p.slot_stride == 0 || sh.frame_off + sh.frame_bytes <= p.out_cap) &&
+                      sh.status != FLACB_E_INTERNAL;
+        if (!sh.writable && sh.status == 0) sh.status = FLACB_E_NOSPACE;
+    }
+    for (int idx = b.tid; idx < STG_WORDS + 4; idx += b.B) b.stg[idx] = 0;
+    __syncthreads();
+
+    /* ---- phase 3: serialise ---- */
+    if (b.tid == 0)
+        for (int i = 0; i < hdr_len; i++) put_serial(b, hdr[i], 8);
+    __syncthreads();
+    for (int c = 0; c < p.channels; c++) {
+        const Decision &d = sh.dec[c];
+        const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
+        if (!lay.xs_all) load_planes(b, c);
+        residual_and_cum<LMAX>(b, x, d);
+        { /* Rice parameters of the chosen order */
+            const int psz = b.n >> d.porder;
+            for (int pi = b.tid; pi < (1 << d.porder); pi += b.B) {
+                const int start = pi * psz < d.warm ? d.warm : pi * psz;
+                const int end = (pi + 1) * psz;
+                const uint32_t len = (uint32_t)(end - start);
+                const u64 sum = cum_at(b, end) - cum_at(b, start);
+                int k = 0;
+                if (sum >= (u64)len && len > 0) {
+                    k = (63 - __clzll(sum)) - (31 - __clz(len));
+                    if (((u64)len << k) > sum) k--;
+                }
+                b.kall[(1u << d.porder) + (uint32_t)pi] = (uint8_t)k;
+            }
+        }
+        /* make sure the serial part fits the window: header byte, warm-up, LPC parameters */
+        if (((sh.pos + 2048u) >> 5) >= sh.wbase + STG_WORDS) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
+        else __syncthreads();
+        if (b.tid == 0) {
+            const uint32_t mask = p.bps >= 32 ? 0xFFFFFFFFu : ((1u << p.bps) - 1u);
+            put_serial(b, d.type ? (0x20u | (uint32_t)(d.order - 1)) << 1 : (0x08u | (uint32_t)d.order) << 1, 8); /* encoder.py:553-569 */
+            for (int i = 0; i < d.warm; i++) put_serial(b, (uint32_t)x[padidx((uint32_t)(GUARD + i))] & mask, p.bps);
+            if (d.type) { /* encoder.py:619-625 */
+                put_serial(b, (uint32_t)(p.P - 1) & 15u, 4);
+                put_serial(b, (uint32_t)d.shift & 31u, 5);
+                const uint32_t pm = (1u << p.P) - 1u;
+                for (int i = 0; i < d.ncoef; i++) put_serial(b, (uint32_t)d.q[i] & pm, p.P);
+            }
+        }
+        __syncthreads();
+        pack_residual(b, d);
+    }
+    /* encoder.py:159-165: pad to a byte, CRC-16 over the whole frame, append big endian */
+    flush_window(b, sh.payload_bytes - sh.wbase * 4u, (sh.payload_bytes + 3u) >> 2);
+    if (b.tid == 0) {
+        if (sh.writable) {
+            uint8_t *dst = p.out + sh.frame_off + sh.payload_bytes;
+            dst[0] = (uint8_t)(sh.crc >> 8);
+            dst[1] = (uint8_t)sh.crc;
+        }
+        p.frame_status[f] = sh.status;
+        if (p.stats) {
+            for (int c = 0; c < p.channels; c++) {
+                if (sh.dec[c].type) atomicAdd(&p.stats[5], 1ull);
+                else atomicAdd(&p.stats[sh.dec[c].order], 1ull);
+            }
+            if (sh.status >= FLACB_E_ASSERT && sh.status <= FLACB_E_ZERODIV) atomicAdd(&p.stats[6], 1ull);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* slot mode (debugging aid): exclusive scan of frame sizes and compaction                 */
+
+__global__ void scan_frame_bytes_kernel(const uint32_t *frame_bytes, u64 *frame_off, uint32_t n)
+{
+    /* single CTA, n is small (frames of one call) */
+    __shared__ u64 carry;
+    __shared__ u64 warp_tot[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const u64 v = i < n ? frame_bytes[i] : 0;
+        u64 inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const u64 t = __shfl_up_sync(FULL, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        u64 wb = 0, tot = 0;
+        for (int w = 0; w < nw; w++) {
+            if (w < warp) wb += warp_tot[w];
+            tot += warp_tot[w];
+        }
+        if (i < n) frame_off[i] = carry + wb + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) frame_off[n] = carry;
+}
+
+__global__ void compact_slots_kernel(const uint8_t *slots, u64 slot_stride, const uint32_t *frame_bytes,
+                                     const u64 *frame_off, uint8_t *out, u64 out_cap, int32_t *frame_status)
+{
+    const uint32_t f = blockIdx.x;
+    const uint32_t nb = frame_bytes[f];
+    const u64 off = frame_off[f];
+    if (off + nb > out_cap) {
+        if (threadIdx.x == 0 && frame_status[f] == 0) frame_status[f] = FLACB_E_NOSPACE;
+        return;
+    }
+    const uint8_t *src = slots + (u64)f * slot_stride;
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
+}
+
+#endif /* !FLACB_HOST_ONLY */
+
+} /* namespace flacb */

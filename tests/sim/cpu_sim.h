@@ -1,0 +1,208 @@
+/*
+ * cpu_sim.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A minimal SIMT simulator so that the device code of flac-py_b200/csrc/flacb200_kernels.cuh
+ * can be executed and checked against the golden vectors on a machine without a GPU.  One CTA
+ * runs at a time; every CUDA thread is a ucontext fiber; __syncthreads and the warp intrinsics
+ * are rendezvous points at which a fiber yields until its peers arrive.  CTAs run in launch
+ * order, so the look-back always finds a published prefix.  Nothing in the product links this.
+ */
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __shared__ static
+#define __constant__
+#define __launch_bounds__(...)
+#define __restrict__
+
+struct sim_dim3 { unsigned x, y, z; };
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
+
+namespace sim {
+
+struct Fiber {
+    ucontext_t ctx;
+    char *stack;
+    bool done;
+};
+
+struct State {
+    ucontext_t main_ctx;
+    std::vector<Fiber> fibers;
+    int cur = 0;
+    int nthreads = 0;
+    int bar_count = 0;
+    unsigned bar_gen = 0;
+    int wbar_count[64];
+    unsigned wbar_gen[64];
+    unsigned long long wbuf[64][32];
+    unsigned char *dyn_smem = nullptr;
+    std::function<void()> body;
+};
+
+inline State &st()
+{
+    static State s;
+    return s;
+}
+
+extern sim_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+inline void yield()
+{
+    State &s = st();
+    swapcontext(&s.fibers[(size_t)s.cur].ctx, &s.main_ctx);
+}
+
+inline void syncthreads()
+{
+    State &s = st();
+    const unsigned g = s.bar_gen;
+    if (++s.bar_count == s.nthreads) {
+        s.bar_count = 0;
+        s.bar_gen++;
+    } else {
+        while (s.bar_gen == g) yield();
+    }
+}
+
+inline void syncwarp()
+{
+    State &s = st();
+    const int w = s.cur >> 5;
+    const unsigned g = s.wbar_gen[w];
+    if (++s.wbar_count[w] == 32) {
+        s.wbar_count[w] = 0;
+        s.wbar_gen[w]++;
+    } else {
+        while (s.wbar_gen[w] == g) yield();
+    }
+}
+
+template <class T>
+inline T exchange(T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "exchange of <= 8 bytes");
+    State &s = st();
+    const int w = s.cur >> 5, lane = s.cur & 31;
+    unsigned long long raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    s.wbuf[w][lane] = raw;
+    syncwarp();
+    T r = v;
+    if (src_lane >= 0 && src_lane < 32) memcpy(&r, &s.wbuf[w][src_lane], sizeof(T));
+    syncwarp();
+    return r;
+}
+
+static void fiber_entry()
+{
+    State &s = st();
+    s.body();
+    s.fibers[(size_t)s.cur].done = true;
+    swapcontext(&s.fibers[(size_t)s.cur].ctx, &s.main_ctx);
+}
+
+/* run one CTA of `nthreads` threads */
+inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_smem_bytes,
+                      const std::function<void()> &body)
+{
+    State &s = st();
+    const size_t stack_bytes = 256 * 1024;
+    s.nthreads = nthreads;
+    s.bar_count = 0;
+    memset(s.wbar_count, 0, sizeof(s.wbar_count));
+    s.body = body;
+    s.dyn_smem = (unsigned char *)aligned_alloc(128, (dyn_smem_bytes + 127) / 128 * 128 + 128);
+    memset(s.dyn_smem, 0xA5, dyn_smem_bytes); /* shared memory is not zero initialised */
+    g_blockIdx = {block, 0, 0};
+    g_gridDim = {grid, 1, 1};
+    g_blockDim = {(unsigned)nthreads, 1, 1};
+    s.fibers.resize((size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        Fiber &f = s.fibers[(size_t)t];
+        f.stack = (char *)malloc(stack_bytes);
+        f.done = false;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = stack_bytes;
+        f.ctx.uc_link = &s.main_ctx;
+        makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    }
+    int alive = nthreads;
+    while (alive > 0) {
+        for (int t = 0; t < nthreads; t++) {
+            Fiber &f = s.fibers[(size_t)t];
+            if (f.done) continue;
+            s.cur = t;
+            g_threadIdx = {(unsigned)t, 0, 0};
+            swapcontext(&s.main_ctx, &f.ctx);
+            if (f.done) alive--;
+        }
+    }
+    for (int t = 0; t < nthreads; t++) free(s.fibers[(size_t)t].stack);
+    free(s.dyn_smem);
+    s.dyn_smem = nullptr;
+}
+
+} /* namespace sim */
+
+#define threadIdx sim::g_threadIdx
+#define blockIdx sim::g_blockIdx
+#define blockDim sim::g_blockDim
+#define gridDim sim::g_gridDim
+
+#define FLACB_DYN_SMEM(name) unsigned char *name = sim::st().dyn_smem
+
+static inline void __syncthreads() { sim::syncthreads(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { sim::syncwarp(); }
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) { sim::yield(); }
+
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return sim::exchange(v, (sim::st().cur & 31) ^ m); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+    const int lane = sim::st().cur & 31;
+    return sim::exchange(v, lane >= (int)d ? lane - (int)d : lane);
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return sim::exchange(v, src & 31); }
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+    sim::State &s = sim::st();
+    const int w = s.cur >> 5, lane = s.cur & 31;
+    s.wbuf[w][lane] = pred ? 1ull : 0ull;
+    sim::syncwarp();
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++)
+        if (s.wbuf[w][l]) r |= 1u << l;
+    sim::syncwarp();
+    return r;
+}
+
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __clzll(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+
+template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> static inline T atomicXor(T *p, T v) { T o = *p; *p = o ^ v; return o; }
+template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }

@@ -1,0 +1,141 @@
+/*
+ * sim_lib.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Runs the device code of flac-py_b200/csrc/flacb200_kernels.cuh on the CPU SIMT simulator
+ * (cpu_sim.h) behind an entry point shaped like flacb_encode_pcm, so that the CPU test suite
+ * can check the kernel logic against the golden vectors and the oracle without a GPU.  It is
+ * slow (a fiber per CUDA thread) and is never loaded by the product.
+ */
+#define FLACB_CPU_SIM 1
+#include "cpu_sim.h"
+
+namespace sim {
+sim_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+}
+
+#include "../../flac-py_b200/csrc/flacb200_host.h"
+#include "../../flac-py_b200/csrc/flacb200_kernels.cuh"
+
+using namespace flacb;
+
+extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int channels, int bits,
+                                int block_size, int max_lpc_order, int qlp_precision, int rice_min,
+                                int rice_max, uint64_t first_frame_number, uint32_t flags,
+                                uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                                uint64_t *frame_offsets, flacb_subframe_info *info,
+                                flacb_stats *stats, int threads_override, uint32_t smem_limit)
+{
+    EncodeArgs a = {n_sample_frames, channels, bits, block_size, max_lpc_order, qlp_precision,
+                    rice_min, rice_max, first_frame_number, flags};
+    int rc = validate_encode_args(a);
+    if (out_len) *out_len = 0;
+    if (rc) return rc;
+    const uint64_t n_frames = (n_sample_frames + (uint64_t)block_size - 1) / (uint64_t)block_size;
+    if (stats) memset(stats, 0, sizeof(*stats)), stats->first_bad_frame = -1;
+    if (n_frames == 0) {
+        if (frame_offsets) frame_offsets[0] = 0;
+        return FLACB_OK;
+    }
+    if (smem_limit == 0) smem_limit = 227 * 1024 - 20 * 1024;
+
+    crc16_table(c_crc16_tab);
+    crc16_xpow_tables(c_xpow_lo, c_xpow_hi, XPOW_HI);
+
+    EncParams p;
+    memset(&p, 0, sizeof(p));
+    p.pcm = (const uint8_t *)pcm;
+    p.n_sample_frames = n_sample_frames;
+    p.channels = channels;
+    p.bps = bits;
+    p.cbytes = (flags & FLACB_PCM_INT32) ? 4 : (bits + 7) / 8;
+    p.block_size = block_size;
+    p.L = max_lpc_order;
+    p.P = qlp_precision;
+    p.rmin = rice_min;
+    p.rmax = rice_max;
+    p.first_frame_number = first_frame_number;
+    p.flags = flags;
+    p.n_frames = (uint32_t)n_frames;
+    p.tail_size = (int)(n_sample_frames - (n_frames - 1) * (uint64_t)block_size);
+    std::vector<double> wf, wt;
+    p.win_full_bad = !tukey_window(block_size, wf, 64);
+    p.win_tail_bad = !tukey_window(p.tail_size, wt, 64);
+    p.win_full = wf.data();
+    p.win_tail = wt.data();
+    p.smem_limit = smem_limit;
+
+    const SmemLayout lay = make_layout(block_size, channels, rice_max, smem_limit);
+    if (lay.total > smem_limit) return FLACB_E_UNSUPPORTED;
+    const int B = threads_override ? threads_override : pick_threads(block_size, E, MAXB);
+
+    std::vector<uint32_t> frame_bytes(n_frames);
+    std::vector<u64> frame_off(n_frames + 1, 0);
+    std::vector<int32_t> frame_status(n_frames, 0);
+    std::vector<u64> lb(n_frames, 0);
+    uint32_t ticket = 0;
+    u64 dstats[8] = {0};
+    std::vector<uint8_t> slots;
+    p.frame_bytes = frame_bytes.data();
+    p.frame_off = frame_off.data();
+    p.frame_status = frame_status.data();
+    p.lb_state = lb.data();
+    p.ticket = &ticket;
+    p.stats = dstats;
+    p.info = info;
+    if (flags & FLACB_SLOT_COMPACT) {
+        p.slot_stride = (frame_bound(block_size, channels, bits, rice_max) + 15) & ~15ull;
+        slots.assign(p.slot_stride * n_frames, 0xEE);
+        p.out = slots.data();
+        p.out_cap = slots.size();
+    } else {
+        p.slot_stride = 0;
+        p.out = out;
+        p.out_cap = out_cap;
+    }
+    for (uint64_t f = 0; f < n_frames; f++) {
+        if (max_lpc_order <= 12)
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<12>(p); });
+        else
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<32>(p); });
+    }
+    if (flags & FLACB_SLOT_COMPACT) {
+        sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(frame_bytes.data(), frame_off.data(), (uint32_t)n_frames); });
+        for (uint64_t f = 0; f < n_frames; f++)
+            sim::run_block((unsigned)f, (unsigned)n_frames, 128, 0, [&]() {
+                compact_slots_kernel(slots.data(), p.slot_stride, frame_bytes.data(), frame_off.data(), out, out_cap,
+                                     frame_status.data());
+            });
+    }
+    uint64_t valid = frame_off[n_frames];
+    for (uint64_t f = 0; f < n_frames; f++) {
+        const int s = frame_status[f];
+        const bool ood = s >= FLACB_E_ASSERT && s <= FLACB_E_ZERODIV;
+        if (s != 0 && !(ood && (flags & FLACB_LENIENT))) {
+            rc = s;
+            valid = frame_off[f];
+            if (stats) stats->first_bad_frame = (int64_t)f;
+            break;
+        }
+    }
+    if (out_len) *out_len = valid;
+    if (frame_offsets) memcpy(frame_offsets, frame_off.data(), sizeof(u64) * (n_frames + 1));
+    if (stats) {
+        stats->frames = n_frames;
+        stats->subframes = n_frames * (uint64_t)channels;
+        for (int o = 0; o < 5; o++) stats->subframes_fixed[o] = dstats[o];
+        stats->subframes_lpc = dstats[5];
+        stats->out_of_domain = dstats[6];
+        stats->bytes_in = n_sample_frames * (uint64_t)channels * (uint64_t)p.cbytes;
+        stats->bytes_out = valid;
+        stats->threads_per_frame = B;
+        stats->smem_bytes = (int32_t)lay.total;
+    }
+    return rc;
+}
+
+extern "C" int flacb_sim_prologue(uint32_t sample_rate, int channels, int bits, uint64_t total_samples,
+                                  int block_size, uint8_t out[42])
+{
+    stream_prologue(sample_rate, channels, bits, total_samples, block_size, out);
+    return 0;
+}
