@@ -1,0 +1,85 @@
+"""`flac.decoder` of the drop-in: same entry point as the reference (flac/decoder.py:31 decode).
+The stream prologue (magic, STREAMINFO, other metadata blocks: decoder.py:34-44, :66-97) is
+parsed on the host; every audio frame -- header, subframes, Rice residuals, prediction restore,
+inter-channel decorrelation (decoder.py:100-498, binary.py:78-141) -- is decoded by
+libflacb200.so on a B200, all frames in parallel."""
+from __future__ import annotations
+
+from io import BufferedIOBase
+from typing import Iterator, Optional, Sequence
+
+import numpy as np
+
+from flac import _native as N
+from flac.binary import Get
+from flac.common import MAGIC, MetadataBlockHeader, MetadataBlockType, Streaminfo
+
+
+def get_metadata_block_header(get: Get) -> MetadataBlockHeader:
+    return MetadataBlockHeader(last=get.bool(), type=MetadataBlockType(get.uint(7)), length=get.uint(24))
+
+
+def get_metadata_block_streaminfo(get: Get) -> Streaminfo:
+    return Streaminfo(
+        min_block_size=get.uint(16), max_block_size=get.uint(16),
+        min_frame_size=get.uint(24), max_frame_size=get.uint(24),
+        sample_rate=get.uint(20), channels=get.uint(3) + 1, sample_size=get.uint(5) + 1,
+        samples=get.uint(36), md5=get.bytes(16))
+
+
+def skip_metadata(get: Get):
+    while True:
+        header = get_metadata_block_header(get)
+        get.bytes(header.length)
+        if header.last is True:
+            return
+
+
+def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,
+                  cap_sample_frames: Optional[int] = None) -> tuple[np.ndarray, int]:
+    """Decode back-to-back audio frames (bytes-like) on the GPU.
+    -> (int32 array (n, frame_channels), frame_channels)"""
+    raw = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else frames
+    ctx = N.default_context(devices[0] if devices else None)
+    cap = cap_sample_frames * 8 if cap_sample_frames else max(raw.size * 16, 1 << 16)
+    while True:
+        out = np.empty(cap, dtype=np.int32)
+        rc, n, fch, _ = ctx.decode_raw(raw.ctypes.data if raw.size else 0, raw.size, sample_size, 0,
+                                       out.ctypes.data, cap)
+        if rc == N.E_NOSPACE:
+            cap *= 4
+            continue
+        N.raise_for_status(rc, "decode")
+        fch = max(fch, 1)
+        return out[:n * fch].reshape(-1, fch), fch
+
+
+def decode(buffer: BufferedIOBase) -> tuple[int, int, int, int, Iterator[list[int]]]:
+    """Reference signature (flac/decoder.py:31-63)."""
+    get = Get(buffer)
+    assert get.bytes(4) == MAGIC
+    header = get_metadata_block_header(get)
+    assert header.type == MetadataBlockType.Streaminfo
+    streaminfo = get_metadata_block_streaminfo(get)
+    if header.last is False:
+        skip_metadata(get)
+
+    def samples() -> Iterator[list[int]]:
+        pcm, _ = decode_frames(buffer.read(), streaminfo.sample_size)
+        for row in pcm.tolist():
+            yield row
+
+    return (streaminfo.sample_rate, streaminfo.sample_size, streaminfo.channels, streaminfo.samples, samples())
+
+
+def decode_pcm(buffer: BufferedIOBase) -> tuple[Streaminfo, np.ndarray]:
+    """Bulk entry used by the CLI: STREAMINFO and the decoded samples as one int32 array."""
+    get = Get(buffer)
+    assert get.bytes(4) == MAGIC
+    header = get_metadata_block_header(get)
+    assert header.type == MetadataBlockType.Streaminfo
+    streaminfo = get_metadata_block_streaminfo(get)
+    if header.last is False:
+        skip_metadata(get)
+    pcm, _ = decode_frames(buffer.read(), streaminfo.sample_size)
+    return streaminfo, pcm

@@ -1,0 +1,149 @@
+"""GPU parity tests proper: the CUDA encode path, called through the package and the C ABI,
+against the golden streams minted from the reference and against the CPU oracle."""
+import numpy as np
+import pytest
+
+import flacb200_synth as S
+import oracle as O
+from helpers import CASES, OOD, case_kwargs, case_pcm, case_stream, hex_f64, ood_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(case):
+    from flac.encoder import EncoderParameters
+    return EncoderParameters(block_size=case["block_size"],
+                             rice_partition_order=range(case["rice_min"], case["rice_max"] + 1),
+                             lpc_order=range(case["max_lpc_order"] + 1),
+                             qlp_precision=case["qlp_precision"])
+
+
+def _encode(x, bits, params, **kw):
+    from flac import _native as N
+    from flac.encoder import encode_frames
+    sh = encode_frames(bits, x.shape[1], S.pack_le(x, bits), params, **kw)[0]
+    if sh.error:
+        raise sh.error
+    return sh, N
+
+
+@pytest.mark.parametrize("mode", ["lookback", "slots"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_stream_bytes(name, mode):
+    case = CASES[name]
+    x = case_pcm(case)
+    from flac import _native as N
+    sh, _ = _encode(x, case["bits"], _params(case), flags=N.SLOT_COMPACT if mode == "slots" else 0)
+    assert sh.rc == 0
+    ref = case_stream(case)
+    assert N.stream_prologue(case["rate"], case["channels"], case["bits"], case["n"], case["block_size"]) == ref[:42]
+    assert sh.out.tobytes() == ref[42:]
+    lens = [4, 4, 34] + [int(b - a) for a, b in zip(sh.offs[:-1], sh.offs[1:])]
+    assert lens == case["chunk_lengths"]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_stage_values(name):
+    """fixed errors, autocorrelation bits, quantised coefficients, LPC errors, Rice decisions"""
+    case = CASES[name]
+    x = case_pcm(case)
+    sh, _ = _encode(x, case["bits"], _params(case), want_info=True)
+    L = case["max_lpc_order"]
+    lags = bad_lags = 0
+    for info, ref in zip(sh.info, case["subframes"]):
+        assert ("lpc" if info.type else "fixed") == ref["type"]
+        assert info.order == ref["order"]
+        assert info.fixed_order == ref["fixed_order"]
+        if ref["fixed_err"] is not None:
+            assert list(info.fixed_err) == ref["fixed_err"]
+        if L > 0:
+            want = [hex_f64(h) for h in ref["autoc"]]
+            got = [info.autoc[i] for i in range(L + 1)]
+            lags += L + 1
+            bad_lags += sum(1 for a, b in zip(got, want) if a != b)
+            if got == want:
+                for m, (qc, shf) in enumerate(ref["quant"]):
+                    assert list(info.lpc_q[m][:info.lpc_ncoef[m]]) == qc
+                    assert info.lpc_shift[m] == shf
+                assert info.lpc_order == ref["lpc_order"]
+                assert info.lpc_err[info.lpc_order - 1] == ref["lpc_total"]
+        assert info.porder == ref["porder"]
+        assert info.method == ref["method"]
+        assert list(info.params[:min(info.nparams, 64)]) == ref["params"][:64]
+    # the double-double accumulation reproduces Python's compensated sum() on every lag seen
+    assert bad_lags == 0, f"{bad_lags}/{lags} autocorrelation lags differ in the last bit"
+
+
+@pytest.mark.parametrize("name", sorted(OOD))
+def test_out_of_domain_raises_like_the_reference(name):
+    case = OOD[name]
+    x = ood_pcm(case)
+    from flac.encoder import encode_pcm
+    with pytest.raises(Exception) as ei:
+        b"".join(encode_pcm(case["rate"], case["bits"], x.shape[1], S.pack_le(x, case["bits"]), _params(case)))
+    assert type(ei.value).__name__ == case["raises"]
+
+
+@pytest.mark.parametrize("name", sorted(OOD))
+def test_out_of_domain_lenient_round_trips(name):
+    case = OOD[name]
+    x = ood_pcm(case)
+    from flac.encoder import encode_pcm
+    stream = b"".join(encode_pcm(case["rate"], case["bits"], x.shape[1], S.pack_le(x, case["bits"]),
+                                 _params(case), strict=False))
+    rate, bits, ch, total, pcm = O.decode_stream(stream)
+    assert (pcm == x).all()
+
+
+def test_module_api_iterator_matches_golden():
+    from flac.encoder import encode
+    case = CASES["c2_white"]
+    x = case_pcm(case)
+    chunks = list(encode(case["rate"], case["bits"], case["channels"], case["n"], iter(x.tolist()), _params(case)))
+    assert [len(c) for c in chunks] == case["chunk_lengths"]
+    assert b"".join(chunks) == case_stream(case)
+
+
+def test_first_frame_number_and_sharding_are_exact():
+    """frames [a, b) encoded separately with their coded numbers concatenate to the whole"""
+    case = CASES["many_frames"]
+    x = case_pcm(case)
+    p = _params(case)
+    whole, _ = _encode(x, case["bits"], p)
+    bs = case["block_size"]
+    cut = 57
+    a, _ = _encode(x[:cut * bs], case["bits"], p)
+    b, _ = _encode(x[cut * bs:], case["bits"], p, first_frame_number=cut)
+    assert a.out.tobytes() + b.out.tobytes() == whole.out.tobytes()
+
+
+@pytest.mark.parametrize("bits,cls,L,bs", [(16, "mixed", 12, 4608), (24, "mixed", 12, 4608), (16, "white", 8, 4096),
+                                           (24, "white", 32, 16384), (16, "mixed", 0, 4608), (8, "white", 6, 1152)])
+def test_against_oracle_on_fresh_inputs(bits, cls, L, bs):
+    x = S.pcm(bs * 9 + bs // 3 + 17, 2, bits, 96000, cls, 4242 + bits + L)
+    if bits == 8:
+        x = (x // 1).astype(np.int32)
+    from flac.encoder import EncoderParameters
+    p = EncoderParameters(block_size=bs, rice_partition_order=range(0, 7), lpc_order=range(L + 1), qlp_precision=7)
+    try:
+        ref = O.encode_frames(x, bits, bs, L, 7, 0, 6)
+    except O.OracleError:
+        pytest.skip("input outside the reference's domain")
+    sh, _ = _encode(x, bits, p)
+    assert sh.rc == 0
+    assert sh.out.tobytes() == ref.data
+    assert (sh.offs == ref.frame_offsets).all()
+
+
+def test_large_config2_slice_round_trip_and_oracle_spot_check():
+    """60 s of config-2 audio: oracle bytes on a slice, oracle decode of the whole"""
+    n = 44100 * 60
+    x = S.pcm(n, 2, 16, 44100, "mixed", 0xF1AC0002)
+    from flac.encoder import EncoderParameters, encode_pcm
+    p = EncoderParameters(block_size=4608, rice_partition_order=range(0, 6), lpc_order=range(13), qlp_precision=5)
+    stream = b"".join(encode_pcm(44100, 16, 2, S.pack_le(x, 16), p))
+    enc = O.encode_frames(x, 16, 4608, 12, 5, 0, 5, threads=16)
+    assert stream[42:] == enc.data
+    rate, bits, ch, total, pcm = O.decode_stream(stream)
+    assert (rate, bits, ch, total) == (44100, 16, 2, n)
+    assert (pcm == x).all()
