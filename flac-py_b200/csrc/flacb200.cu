@@ -472,9 +472,127 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
                                    uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
                                    int *frame_channels, flacb_stats *stats)
 {
-    (void)c, (void)frames, (void)len, (void)streaminfo_bits, (void)flags, (void)pcm_out, (void)cap_samples;
     if (n_sample_frames) *n_sample_frames = 0;
     if (frame_channels) *frame_channels = 0;
-    if (stats) memset(stats, 0, sizeof(*stats));
-    return FLACB_E_NOTIMPL;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->first_bad_frame = -1;
+    }
+    if (!c || (!frames && len)) return FLACB_E_ASSERT;
+    if (len < 2) return FLACB_OK; /* decoder.py:104-108: EOFError ends the frame loop */
+    if (len >= (1ull << 40)) return FLACB_E_UNSUPPORTED;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f;
+    const uint8_t *d_s = frames;
+    if (!(flags & FLACB_INPUT_ON_DEVICE)) {
+        if ((rc = c->d_stream.ensure(len))) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_c0, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_stream.p, frames, len, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_c1, c->stream));
+        d_s = (const uint8_t *)c->d_stream.p;
+    }
+    /* D1: sync candidates in stream order */
+    const u64 n_chunks = (len + SYNC_CHUNK - 1) / SYNC_CHUNK;
+    if (n_chunks > 0x7FFFFFFFull) return FLACB_E_UNSUPPORTED;
+    /* d_dmisc: [counts u32 n_chunks][offsets u64 n_chunks + 1][result] */
+    const size_t off_counts = 0;
+    const size_t off_offsets = (n_chunks * 4 + 15) & ~(size_t)15;
+    const size_t off_result = off_offsets + (n_chunks + 1) * 8;
+    if ((rc = c->d_dmisc.ensure(off_result + sizeof(DecodeResult) + 64))) return rc;
+    uint8_t *dm = (uint8_t *)c->d_dmisc.p;
+    uint32_t *d_counts = (uint32_t *)(dm + off_counts);
+    u64 *d_offsets = (u64 *)(dm + off_offsets);
+    DecodeResult *d_res = (DecodeResult *)(dm + off_result);
+    if ((rc = c->h_dmeta.ensure(256))) return rc;
+    u64 *h_u64 = (u64 *)c->h_dmeta.p;
+
+    CUDA_TRY(cudaEventRecord(c->ev_k0, c->stream));
+    find_sync_kernel<<<(unsigned)n_chunks, SYNC_THREADS, 0, c->stream>>>(d_s, len, d_counts, d_offsets, nullptr, 0);
+    scan_frame_bytes_kernel<<<1, 256, 0, c->stream>>>(d_counts, d_offsets, (uint32_t)n_chunks);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_u64, d_offsets + n_chunks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const u64 n_cand = h_u64[0];
+    if (n_cand == 0) return len >= 2 ? FLACB_E_ASSERT : FLACB_OK; /* decoder.py:137: no sync at the start */
+    if (n_cand > 0x7FFFFFF0ull) return FLACB_E_UNSUPPORTED;
+    /* d_cand: [Candidate n][sizes u32 n][tmp_off u64 n + 1][jump u32 2n][reach u32 n] */
+    const size_t o_sizes = n_cand * sizeof(Candidate);
+    const size_t o_tmpoff = (o_sizes + n_cand * 4 + 15) & ~(size_t)15;
+    const size_t o_jump = o_tmpoff + (n_cand + 1) * 8;
+    const size_t o_reach = o_jump + 2 * n_cand * 4;
+    if ((rc = c->d_cand.ensure(o_reach + n_cand * 4 + 64))) return rc;
+    uint8_t *dc = (uint8_t *)c->d_cand.p;
+    Candidate *d_cand = (Candidate *)dc;
+    uint32_t *d_sizes = (uint32_t *)(dc + o_sizes);
+    u64 *d_tmpoff = (u64 *)(dc + o_tmpoff);
+    uint32_t *d_jump = (uint32_t *)(dc + o_jump);
+    uint32_t *d_reach = (uint32_t *)(dc + o_reach);
+    find_sync_kernel<<<(unsigned)n_chunks, SYNC_THREADS, 0, c->stream>>>(d_s, len, d_counts, d_offsets, d_cand, 1);
+    /* D2: headers, then the scratch layout */
+    parse_headers_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, c->stream>>>(d_s, len, streaminfo_bits, d_cand,
+                                                                                  (uint32_t)n_cand, d_sizes);
+    scan_frame_bytes_kernel<<<1, 256, 0, c->stream>>>(d_sizes, d_tmpoff, (uint32_t)n_cand);
+    g_launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_u64, d_tmpoff + n_cand, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const u64 tmp_samples = h_u64[0];
+    if ((rc = c->d_frames.ensure((tmp_samples + 16) * 4))) return rc;
+    int32_t *d_tmp = (int32_t *)c->d_frames.p;
+    /* D3 + D4 */
+    decode_frames_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
+                                                                                  d_tmpoff, d_tmp);
+    chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    DecodeResult *h_res = (DecodeResult *)(h_u64 + 8);
+    CUDA_TRY(cudaMemcpyAsync(h_res, d_res, sizeof(DecodeResult), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const u64 nsf = h_res->n_sample_frames;
+    const int fch = h_res->frame_channels;
+    rc = h_res->status;
+    const u64 total = nsf * (u64)(fch > 0 ? fch : 1);
+    if (total > cap_samples) {
+        CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
+        return FLACB_E_NOSPACE;
+    }
+    int32_t *d_out = pcm_out;
+    if (!(flags & FLACB_OUTPUT_ON_DEVICE)) {
+        if ((rc = c->d_pcm.ensure((total + 16) * 4))) return rc;
+        d_out = (int32_t *)c->d_pcm.p;
+        rc = h_res->status;
+    }
+    if (total) {
+        interleave_kernel<<<(unsigned)n_cand, 256, 0, c->stream>>>(d_cand, d_tmp, d_out, total, fch);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
+    if (!(flags & FLACB_OUTPUT_ON_DEVICE) && total) {
+        CUDA_TRY(cudaEventRecord(c->ev_c0, c->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpyAsync(pcm_out, d_out, total * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_c1, c->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+        CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c->ev_c0, c->ev_c1));
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    CUDA_TRY(cudaEventElapsedTime(&k_ms, c->ev_k0, c->ev_k1));
+    if (n_sample_frames) *n_sample_frames = nsf;
+    if (frame_channels) *frame_channels = fch;
+    if (stats) {
+        stats->frames = h_res->n_frames;
+        stats->subframes = h_res->n_frames * (u64)(fch > 0 ? fch : 0);
+        stats->bytes_in = len;
+        stats->bytes_out = total * 4;
+        stats->first_bad_frame = rc ? (int64_t)h_res->n_frames : -1;
+        stats->kernel_ms = k_ms;
+        stats->h2d_ms = h2d_ms;
+        stats->d2h_ms = d2h_ms;
+        stats->out_of_domain = n_cand - h_res->n_frames; /* sync candidates that were not frames */
+    }
+    return rc;
 }

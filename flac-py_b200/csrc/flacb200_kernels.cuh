@@ -48,7 +48,10 @@ typedef long long i64;
 constexpr int E = 8;            /* consecutive samples per thread per tile */
 constexpr int GUARD = 32;       /* zero history in front of every channel plane */
 constexpr int TAILPAD = 48;     /* zero samples behind a plane (window reads run past the end) */
-constexpr int STG_WORDS = 4096; /* staging window of the bit packer, 32-bit words */
+#ifndef FLACB_STG_WORDS
+#define FLACB_STG_WORDS 4096
+#endif
+constexpr int STG_WORDS = FLACB_STG_WORDS; /* staging window of the bit packer, 32-bit words */
 constexpr int MAXB = 576;       /* threads per CTA, upper bound */
 constexpr int MAX_CH = 8;
 constexpr int MAX_CAND = 16;    /* Rice partition orders 0..15 */

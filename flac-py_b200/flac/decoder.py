@@ -35,10 +35,11 @@ def skip_metadata(get: Get):
             return
 
 
-def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,
-                  cap_sample_frames: Optional[int] = None) -> tuple[np.ndarray, int]:
+def decode_frames_status(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,
+                         cap_sample_frames: Optional[int] = None) -> tuple[np.ndarray, int, int]:
     """Decode back-to-back audio frames (bytes-like) on the GPU.
-    -> (int32 array (n, frame_channels), frame_channels)"""
+    -> (int32 array (n, frame_channels), frame_channels, status): the samples of the frames in
+    front of the first one the reference decoder fails in, and that failure's status."""
     raw = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else frames
     ctx = N.default_context(devices[0] if devices else None)
     cap = cap_sample_frames * 8 if cap_sample_frames else max(raw.size * 16, 1 << 16)
@@ -49,9 +50,18 @@ def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] 
         if rc == N.E_NOSPACE:
             cap *= 4
             continue
-        N.raise_for_status(rc, "decode")
+        if rc in (N.E_CUDA, N.E_UNSUPPORTED, N.E_INTERNAL):
+            N.raise_for_status(rc, "decode")
         fch = max(fch, 1)
-        return out[:n * fch].reshape(-1, fch), fch
+        return out[:n * fch].reshape(-1, fch), fch, rc
+
+
+def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,
+                  cap_sample_frames: Optional[int] = None) -> tuple[np.ndarray, int]:
+    """-> (int32 array (n, frame_channels), frame_channels); raises what the reference raises."""
+    pcm, fch, rc = decode_frames_status(frames, sample_size, devices=devices, cap_sample_frames=cap_sample_frames)
+    N.raise_for_status(rc, "decode")
+    return pcm, fch
 
 
 def decode(buffer: BufferedIOBase) -> tuple[int, int, int, int, Iterator[list[int]]]:
@@ -65,9 +75,12 @@ def decode(buffer: BufferedIOBase) -> tuple[int, int, int, int, Iterator[list[in
         skip_metadata(get)
 
     def samples() -> Iterator[list[int]]:
-        pcm, _ = decode_frames(buffer.read(), streaminfo.sample_size)
+        # like the reference's generator: the sample frames of the good frames first, then the
+        # exception of the frame that fails
+        pcm, _, rc = decode_frames_status(buffer.read(), streaminfo.sample_size)
         for row in pcm.tolist():
             yield row
+        N.raise_for_status(rc, "decode")
 
     return (streaminfo.sample_rate, streaminfo.sample_size, streaminfo.channels, streaminfo.samples, samples())
 

@@ -15,6 +15,7 @@ sim_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
 #include "../../flac-py_b200/csrc/flacb200_host.h"
 #include "../../flac-py_b200/csrc/flacb200_kernels.cuh"
+#include "../../flac-py_b200/csrc/flacb200_decode.cuh"
 
 using namespace flacb;
 
@@ -138,4 +139,49 @@ extern "C" int flacb_sim_prologue(uint32_t sample_rate, int channels, int bits, 
 {
     stream_prologue(sample_rate, channels, bits, total_samples, block_size, out);
     return 0;
+}
+
+/* flacb_decode_frames on the simulator (same kernel sequence as flacb200.cu) */
+extern "C" int flacb_sim_decode(const uint8_t *frames, uint64_t len, int streaminfo_bits, int32_t *pcm_out,
+                                uint64_t cap_samples, uint64_t *n_sample_frames, int *frame_channels,
+                                uint64_t *n_candidates)
+{
+    if (n_sample_frames) *n_sample_frames = 0;
+    if (frame_channels) *frame_channels = 0;
+    if (n_candidates) *n_candidates = 0;
+    if (len < 2) return FLACB_OK;
+    const u64 n_chunks = (len + SYNC_CHUNK - 1) / SYNC_CHUNK;
+    std::vector<uint32_t> counts(n_chunks);
+    std::vector<u64> offsets(n_chunks + 1);
+    for (u64 b = 0; b < n_chunks; b++)
+        sim::run_block((unsigned)b, (unsigned)n_chunks, SYNC_THREADS, 0,
+                       [&]() { find_sync_kernel(frames, len, counts.data(), offsets.data(), nullptr, 0); });
+    sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(counts.data(), offsets.data(), (uint32_t)n_chunks); });
+    const u64 n_cand = offsets[n_chunks];
+    if (n_candidates) *n_candidates = n_cand;
+    if (n_cand == 0) return FLACB_E_ASSERT;
+    std::vector<Candidate> cand(n_cand);
+    std::vector<uint32_t> sizes(n_cand), jump(2 * n_cand), reach(n_cand);
+    std::vector<u64> tmpoff(n_cand + 1);
+    for (u64 b = 0; b < n_chunks; b++)
+        sim::run_block((unsigned)b, (unsigned)n_chunks, SYNC_THREADS, 0,
+                       [&]() { find_sync_kernel(frames, len, counts.data(), offsets.data(), cand.data(), 1); });
+    const unsigned nb = (unsigned)((n_cand + 127) / 128);
+    for (unsigned b = 0; b < nb; b++)
+        sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data()); });
+    sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
+    std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
+    for (unsigned b = 0; b < nb; b++)
+        sim::run_block(b, nb, 128, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data()); });
+    DecodeResult res;
+    sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
+    const u64 total = res.n_sample_frames * (u64)(res.frame_channels > 0 ? res.frame_channels : 1);
+    if (total > cap_samples) return FLACB_E_NOSPACE;
+    if (total)
+        for (u64 b = 0; b < n_cand; b++)
+            sim::run_block((unsigned)b, (unsigned)n_cand, 256, 0,
+                           [&]() { interleave_kernel(cand.data(), tmp.data(), pcm_out, total, res.frame_channels); });
+    if (n_sample_frames) *n_sample_frames = res.n_sample_frames;
+    if (frame_channels) *frame_channels = res.frame_channels;
+    return res.status;
 }

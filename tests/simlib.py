@@ -52,24 +52,34 @@ class SubframeInfo(C.Structure):
     ]
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, small_window: bool = False) -> str:
+    """small_window: a variant with a 256-word staging window, so that tests reach the packer's
+    multi-pass path (with the product's 4096 words a tile can never outgrow the window)."""
     srcs = [os.path.join(_SIM, "sim_lib.cpp"), os.path.join(_SIM, "cpu_sim.h"),
             os.path.join(_ROOT, "flac-py_b200", "csrc", "flacb200_kernels.cuh"),
             os.path.join(_ROOT, "flac-py_b200", "csrc", "flacb200_host.h"),
             os.path.join(_ROOT, "include", "flacb200.h")]
-    stale = not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs)
+    srcs.append(os.path.join(_ROOT, "flac-py_b200", "csrc", "flacb200_decode.cuh"))
+    target = _LIB.replace(".so", "_smallwin.so") if small_window else _LIB
+    stale = not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
+        extra = ["-DFLACB_STG_WORDS=256"] if small_window else []
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", _SIM,
-                        "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
-                        "-o", _LIB, srcs[0]], check=True)
-    return _LIB
+                        "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", *extra,
+                        "-o", target, srcs[0]], check=True)
+    return target
 
 
 _lib = None
+_libs = {}
 
 
-def lib():
+def lib(small_window: bool = False):
     global _lib
+    if small_window:
+        if "small" not in _libs:
+            _libs["small"] = _declare(C.CDLL(build(small_window=True)))
+        return _libs["small"]
     if _lib is None:
         build()
         L = C.CDLL(_LIB)
@@ -80,6 +90,15 @@ def lib():
             C.POINTER(SubframeInfo), C.POINTER(Stats), C.c_int, C.c_uint32]
         _lib = L
     return _lib
+
+
+def _declare(L):
+    L.flacb_sim_encode.restype = C.c_int
+    L.flacb_sim_encode.argtypes = [
+        C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
+        C.POINTER(SubframeInfo), C.POINTER(Stats), C.c_int, C.c_uint32]
+    return L
 
 
 def pack_pcm(pcm: np.ndarray, bits: int) -> np.ndarray:
@@ -97,7 +116,8 @@ def pack_pcm(pcm: np.ndarray, bits: int) -> np.ndarray:
 def encode_frames(pcm: np.ndarray, bits: int, block_size: int, max_lpc_order: int = 12,
                   qlp_precision: int = 5, rice_min: int = 0, rice_max: int = 5,
                   first_frame_number: int = 0, flags: int = 0, want_info: bool = False,
-                  threads: int = 0, smem_limit: int = 0, int32_input: bool = False):
+                  threads: int = 0, smem_limit: int = 0, int32_input: bool = False,
+                  small_window: bool = False):
     """-> (status, data, frame_offsets, info list | None, Stats)"""
     n, ch = pcm.shape
     if int32_input:
@@ -113,8 +133,24 @@ def encode_frames(pcm: np.ndarray, bits: int, block_size: int, max_lpc_order: in
     out_len = C.c_uint64(0)
     info = (SubframeInfo * max(nfr * ch, 1))() if want_info else None
     st = Stats()
-    rc = lib().flacb_sim_encode(raw.ctypes.data, n, ch, bits, block_size, max_lpc_order,
+    rc = lib(small_window).flacb_sim_encode(raw.ctypes.data, n, ch, bits, block_size, max_lpc_order,
                                 qlp_precision, rice_min, rice_max, first_frame_number, flags,
                                 out.ctypes.data, cap, C.byref(out_len), offs.ctypes.data, info,
                                 C.byref(st), threads, smem_limit)
     return rc, out[:out_len.value].tobytes(), offs, (list(info)[:nfr * ch] if info else None), st
+
+
+def decode_frames(frames: bytes, streaminfo_bits: int, cap_samples: int | None = None):
+    """-> (status, pcm int32 (n, frame_channels), frame_channels, n_candidates)"""
+    L = lib()
+    L.flacb_sim_decode.restype = C.c_int
+    L.flacb_sim_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    raw = np.frombuffer(frames, dtype=np.uint8)
+    cap = cap_samples or max(len(frames) * 16, 1 << 16)
+    out = np.zeros(cap, dtype=np.int32)
+    n, fch, nc = C.c_uint64(0), C.c_int(0), C.c_uint64(0)
+    rc = L.flacb_sim_decode(raw.ctypes.data if raw.size else None, raw.size, streaminfo_bits,
+                            out.ctypes.data, cap, C.byref(n), C.byref(fch), C.byref(nc))
+    f = max(fch.value, 1)
+    return rc, out[:n.value * f].reshape(-1, f).copy(), fch.value, nc.value

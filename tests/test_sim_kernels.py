@@ -1,0 +1,110 @@
+"""The CUDA kernels' logic, run on the CPU SIMT simulator (tests/sim), against the golden streams.
+
+This is what `-m "not gpu"` can say about the device code on a machine without a GPU; the real
+parity tests (tests/test_gpu_*.py) run the same comparisons on the B200."""
+import numpy as np
+import pytest
+
+import oracle as O
+import simlib
+from helpers import CASES, OOD, case_kwargs, case_pcm, case_stream, ood_pcm
+
+FAST = ["c1_sine", "c2_white", "c2_silence", "c2_clip", "bs1000", "bs255", "bs192_r0", "q8_white", "q15_white24",
+        "c3_white", "c4_mixed"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_sim_encode_matches_golden(name):
+    case = CASES[name]
+    x = case_pcm(case)
+    rc, data, offs, _, st = simlib.encode_frames(x, case["bits"], **case_kwargs(case))
+    assert rc == 0
+    assert data == case_stream(case)[42:]
+    lens = [4, 4, 34] + [int(b - a) for a, b in zip(offs[:-1], offs[1:])]
+    assert lens == case["chunk_lengths"]
+
+
+@pytest.mark.parametrize("name", ["c2_white", "bs255", "c1_sine"])
+def test_sim_slot_mode_and_single_plane_mode(name):
+    case = CASES[name]
+    x = case_pcm(case)
+    ref = case_stream(case)[42:]
+    rc, data, _, _, _ = simlib.encode_frames(x, case["bits"], flags=simlib.FLAG_SLOT_COMPACT, **case_kwargs(case))
+    assert rc == 0 and data == ref
+    # a shared memory budget that only fits one channel plane: planes are reloaded per channel
+    rc, data, _, _, st = simlib.encode_frames(x, case["bits"], smem_limit=72 * 1024, **case_kwargs(case))
+    assert rc == 0 and data == ref
+
+
+def test_sim_other_thread_counts_and_int32_input():
+    case = CASES["c2_white"]
+    x = case_pcm(case)
+    ref = case_stream(case)[42:]
+    for threads in (64, 192, 320):  # several tiles per block, partly filled last tile
+        rc, data, _, _, _ = simlib.encode_frames(x, 16, threads=threads, **case_kwargs(case))
+        assert rc == 0 and data == ref, threads
+    rc, data, _, _, _ = simlib.encode_frames(x, 16, int32_input=True, **case_kwargs(case))
+    assert rc == 0 and data == ref
+
+
+def test_sim_long_unary_runs_cross_the_staging_window():
+    """spikes in near-silence make Rice codes hundreds of bits long; with a 256-word staging
+    window (test build) a tile's codes span many windows: the packer's multi-pass path"""
+    rng = np.random.default_rng(3)
+    x = rng.integers(-2, 3, size=(4608 * 2, 2)).astype(np.int32)
+    x[100::173] = 30000
+    x[77::911, 1] = -32768
+    ref = O.encode_frames(x, 16, 4608, 12, 5, 0, 0)
+    for small in (False, True):
+        rc, data, offs, _, _ = simlib.encode_frames(x, 16, 4608, 12, 5, 0, 0, small_window=small)
+        assert rc == 0 and data == ref.data, small
+    case = CASES["c2_white"]
+    rc, data, _, _, _ = simlib.encode_frames(case_pcm(case), 16, small_window=True, **case_kwargs(case))
+    assert rc == 0 and data == case_stream(case)[42:]
+
+
+@pytest.mark.parametrize("name", sorted(OOD))
+def test_sim_out_of_domain_status_and_lenient_stream(name):
+    case = OOD[name]
+    x = ood_pcm(case)
+    kw = {k: case[k] for k in ("block_size", "max_lpc_order", "qlp_precision", "rice_min", "rice_max")}
+    rc, data, offs, _, st = simlib.encode_frames(x, case["bits"], **kw)
+    names = {1: "AssertionError", 2: "ValueError", 3: "ZeroDivisionError"}
+    assert names.get(rc) == case["raises"]
+    rc, data, offs, _, st = simlib.encode_frames(x, case["bits"], flags=simlib.FLAG_LENIENT, **kw)
+    assert rc == 0 and st.out_of_domain >= 1
+    stream = O.stream_prologue(case["rate"], 2, case["bits"], x.shape[0], case["block_size"]) + data
+    assert (O.decode_stream(stream)[4] == x).all()
+
+
+def test_sim_first_frame_number():
+    case = CASES["bs192_r0"]
+    x = case_pcm(case)
+    kw = case_kwargs(case)
+    ref = O.encode_frames(x, 16, first_frame_number=1000, **kw)
+    rc, data, _, _, _ = simlib.encode_frames(x, 16, first_frame_number=1000, **kw)
+    assert rc == 0 and data == ref.data
+
+
+@pytest.mark.parametrize("name", ["c2_white", "many_frames", "c3_white", "bs255", "c1_sine", "c4_white"])
+def test_sim_decode_matches_oracle(name):
+    case = CASES[name]
+    s = case_stream(case)
+    rc, pcm, fch, ncand = simlib.decode_frames(s[42:], case["bits"])
+    try:
+        ref = O.decode_stream(s)[4]
+        assert rc == 0 and pcm.shape == ref.shape and (pcm == ref).all()
+        assert (pcm == case_pcm(case)).all()
+    except O.OracleError as e:
+        assert rc == e.code
+
+
+def test_sim_decode_truncated_and_garbage():
+    case = CASES["c2_white"]
+    s = case_stream(case)[42:]
+    rc, pcm, fch, _ = simlib.decode_frames(s[:-100], 16)
+    assert rc == 0 and pcm.shape == (4608 * 3, 2)
+    rc, pcm, fch, _ = simlib.decode_frames(b"\x00" * 100 + s, 16)  # no sync at the start
+    assert rc == 1 and pcm.shape[0] == 0
+    rc, pcm, fch, _ = simlib.decode_frames(s + b"\x12\x34\x56", 16)  # junk behind the last frame
+    assert rc == 1 and pcm.shape == (14688, 2)
