@@ -277,7 +277,15 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     const SmemLayout lay = make_layout(a.block_size, a.channels, a.rice_max, smem_limit);
     if (lay.total > smem_limit) return FLACB_E_UNSUPPORTED;
     if (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) >= (u64)XPOW_HI * 256) return FLACB_E_UNSUPPORTED;
-    const int B = pick_threads(a.block_size, E, MAXB);
+    /* two CTAs per SM whenever shared memory allows it: the kernel is latency bound (serial
+     * Levinson, barriers), a second resident frame hides that (measured: profiles/) */
+    const size_t per_sm = 228 * 1024;
+    const bool two_per_sm = 2 * ((size_t)lay.total + static_smem + 1024) <= per_sm;
+    int B = pick_threads(a.block_size, E, two_per_sm ? MAXB / 2 : MAXB);
+    if (const char *e = getenv("FLACB200_THREADS")) { /* tuning knob: threads per frame */
+        const int v = atoi(e);
+        if (v >= 32 && v <= MAXB && v % 32 == 0) B = v;
+    }
 
     int rc;
     if ((rc = upload_window(c, a.block_size, c->win_full, c->win_full_n, c->win_full_ok))) return rc;
@@ -468,9 +476,9 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
 
 /* ------------------------------------------------------------------------------------- */
 
-extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
-                                   uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
-                                   int *frame_channels, flacb_stats *stats)
+static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
+                              uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
+                              int *frame_channels, flacb_stats *stats, int check_crc8)
 {
     if (n_sample_frames) *n_sample_frames = 0;
     if (frame_channels) *frame_channels = 0;
@@ -532,7 +540,7 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
     find_sync_kernel<<<(unsigned)n_chunks, SYNC_THREADS, 0, c->stream>>>(d_s, len, d_counts, d_offsets, d_cand, 1);
     /* D2: headers, then the scratch layout */
     parse_headers_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, c->stream>>>(d_s, len, streaminfo_bits, d_cand,
-                                                                                  (uint32_t)n_cand, d_sizes);
+                                                                                  (uint32_t)n_cand, d_sizes, check_crc8);
     scan_frame_bytes_kernel<<<1, 256, 0, c->stream>>>(d_sizes, d_tmpoff, (uint32_t)n_cand);
     g_launches += 3;
     CUDA_TRY(cudaGetLastError());
@@ -542,8 +550,8 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
     if ((rc = c->d_frames.ensure((tmp_samples + 16) * 4))) return rc;
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
-    decode_frames_kernel<<<(unsigned)((n_cand + 127) / 128), 128, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
-                                                                                  d_tmpoff, d_tmp);
+    decode_frames_kernel<<<(unsigned)((n_cand + 31) / 32), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
+                                                                               d_tmpoff, d_tmp);
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -553,6 +561,7 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
     const u64 nsf = h_res->n_sample_frames;
     const int fch = h_res->frame_channels;
     rc = h_res->status;
+    if (rc == STATUS_CRC8_MISMATCH) return rc; /* the chain reached a frame with a bad header CRC: caller retries unfiltered */
     const u64 total = nsf * (u64)(fch > 0 ? fch : 1);
     if (total > cap_samples) {
         CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
@@ -594,5 +603,21 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
         stats->d2h_ms = d2h_ms;
         stats->out_of_domain = n_cand - h_res->n_frames; /* sync candidates that were not frames */
     }
+    return rc;
+}
+
+extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
+                                   uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
+                                   int *frame_channels, flacb_stats *stats)
+{
+    /* fast path: sync candidates must carry a valid header CRC-8.  The reference does not verify
+     * CRCs (decoder.py:175), so if the frame chain runs into a frame whose CRC-8 is wrong the
+     * decode is repeated with every sync pattern as a candidate, which is exactly the reference's
+     * behaviour (at the price of parsing the false candidates too). */
+    int rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, pcm_out, cap_samples, n_sample_frames,
+                                frame_channels, stats, 1);
+    if (rc == STATUS_CRC8_MISMATCH)
+        rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, pcm_out, cap_samples, n_sample_frames,
+                                frame_channels, stats, 0);
     return rc;
 }

@@ -245,8 +245,13 @@ __device__ int parse_frame_header(BitReader &g, int si_bits, Candidate &c)
     return FLACB_OK;
 }
 
+/* Status of a candidate whose header CRC-8 does not match.  The reference never checks the
+ * CRC (decoder.py:175), so such a candidate is only skipped on the fast path: if the frame chain
+ * ever lands on one, the host repeats the decode without the filter. */
+constexpr int STATUS_CRC8_MISMATCH = 101;
+
 __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Candidate *cand, uint32_t n_cand,
-                                     uint32_t *sizes)
+                                     uint32_t *sizes, int check_crc8)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
@@ -255,6 +260,17 @@ __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Can
     g.init(s, len, c.start);
     c.status = parse_frame_header(g, si_bits, c);
     c.hdr_bits = (uint32_t)(g.bit_pos() - c.start * 8);
+    if (c.status == FLACB_OK && check_crc8) {
+        /* sync patterns inside Rice data almost never carry a valid header CRC (crc.py:17-22);
+         * dropping them here keeps garbage "frames" with huge block sizes off the GPU */
+        const uint32_t nb = c.hdr_bits / 8;
+        uint32_t crc = 0;
+        for (uint32_t i = 0; i + 1 < nb; i++) {
+            crc ^= s[c.start + i];
+            for (int bit = 0; bit < 8; bit++) crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xFFu : (crc << 1) & 0xFFu;
+        }
+        if (crc != s[c.start + nb - 1]) c.status = STATUS_CRC8_MISMATCH;
+    }
     if (c.status != FLACB_OK) c.bs = 0, c.nch = 0;
     cand[i] = c;
     sizes[i] = (uint32_t)c.bs * (uint32_t)c.nch;
@@ -388,7 +404,7 @@ __device__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *o
     return FLACB_OK;
 }
 
-__global__ void __launch_bounds__(128) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
+__global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
                                                             const u64 *tmp_off, int32_t *tmp)
 {
     const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;

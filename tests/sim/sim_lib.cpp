@@ -142,9 +142,9 @@ extern "C" int flacb_sim_prologue(uint32_t sample_rate, int channels, int bits, 
 }
 
 /* flacb_decode_frames on the simulator (same kernel sequence as flacb200.cu) */
-extern "C" int flacb_sim_decode(const uint8_t *frames, uint64_t len, int streaminfo_bits, int32_t *pcm_out,
-                                uint64_t cap_samples, uint64_t *n_sample_frames, int *frame_channels,
-                                uint64_t *n_candidates)
+static int sim_decode_impl(const uint8_t *frames, uint64_t len, int streaminfo_bits, int32_t *pcm_out,
+                           uint64_t cap_samples, uint64_t *n_sample_frames, int *frame_channels,
+                           uint64_t *n_candidates, int check_crc8)
 {
     if (n_sample_frames) *n_sample_frames = 0;
     if (frame_channels) *frame_channels = 0;
@@ -168,13 +168,14 @@ extern "C" int flacb_sim_decode(const uint8_t *frames, uint64_t len, int streami
                        [&]() { find_sync_kernel(frames, len, counts.data(), offsets.data(), cand.data(), 1); });
     const unsigned nb = (unsigned)((n_cand + 127) / 128);
     for (unsigned b = 0; b < nb; b++)
-        sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data()); });
+        sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data(), check_crc8); });
     sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
     std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
     for (unsigned b = 0; b < nb; b++)
         sim::run_block(b, nb, 128, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data()); });
     DecodeResult res;
     sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
+    if (res.status == STATUS_CRC8_MISMATCH) return res.status;
     const u64 total = res.n_sample_frames * (u64)(res.frame_channels > 0 ? res.frame_channels : 1);
     if (total > cap_samples) return FLACB_E_NOSPACE;
     if (total)
@@ -184,4 +185,16 @@ extern "C" int flacb_sim_decode(const uint8_t *frames, uint64_t len, int streami
     if (n_sample_frames) *n_sample_frames = res.n_sample_frames;
     if (frame_channels) *frame_channels = res.frame_channels;
     return res.status;
+}
+
+extern "C" int flacb_sim_decode(const uint8_t *frames, uint64_t len, int streaminfo_bits, int32_t *pcm_out,
+                                uint64_t cap_samples, uint64_t *n_sample_frames, int *frame_channels,
+                                uint64_t *n_candidates)
+{
+    int rc = sim_decode_impl(frames, len, streaminfo_bits, pcm_out, cap_samples, n_sample_frames, frame_channels,
+                             n_candidates, 1);
+    if (rc == STATUS_CRC8_MISMATCH)
+        rc = sim_decode_impl(frames, len, streaminfo_bits, pcm_out, cap_samples, n_sample_frames, frame_channels,
+                             n_candidates, 0);
+    return rc;
 }

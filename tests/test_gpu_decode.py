@@ -105,3 +105,19 @@ def test_cli_encode_decode_round_trip(tmp_path):
     with wave.open(str(wav_out), "rb") as w:
         assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, 2, 44100, x.shape[0])
         assert w.readframes(w.getnframes()) == S.pack_le(x, 16)
+
+
+def test_decode_ignores_crcs_like_the_reference():
+    """a wrong header CRC-8 / frame CRC-16 does not stop the reference (decoder.py:128, :175):
+    the CRC-8 filter of the fast path must fall back to the unfiltered scan"""
+    from flac.decoder import decode_frames
+    case = CASES["c2_white"]
+    stream = bytearray(case_stream(case))
+    from helpers import case_kwargs
+    enc = O.encode_frames(case_pcm(case), 16, **case_kwargs(case))
+    f1 = 42 + int(enc.frame_offsets[1])
+    stream[f1 + 5] ^= 0x5A
+    stream[-1] ^= 0xFF
+    ref = O.decode_stream(bytes(stream))[4]
+    pcm, fch = decode_frames(bytes(stream[42:]), 16)
+    assert pcm.shape == ref.shape and (pcm == ref).all()

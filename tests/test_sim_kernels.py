@@ -108,3 +108,17 @@ def test_sim_decode_truncated_and_garbage():
     assert rc == 1 and pcm.shape[0] == 0
     rc, pcm, fch, _ = simlib.decode_frames(s + b"\x12\x34\x56", 16)  # junk behind the last frame
     assert rc == 1 and pcm.shape == (14688, 2)
+
+
+def test_sim_decode_ignores_crcs_like_the_reference():
+    """a frame with a wrong header CRC-8 / frame CRC-16 still decodes (decoder.py:128, :175)"""
+    case = CASES["c2_white"]
+    stream = bytearray(case_stream(case))
+    enc = O.encode_frames(case_pcm(case), 16, **case_kwargs(case))
+    f1 = 42 + int(enc.frame_offsets[1])
+    assert stream[f1:f1 + 2] == b"\xff\xf8"
+    stream[f1 + 5] ^= 0x5A          # CRC-8 of frame 1
+    stream[-1] ^= 0xFF              # CRC-16 of the last frame
+    ref = O.decode_stream(bytes(stream))[4]
+    rc, pcm, fch, _ = simlib.decode_frames(bytes(stream[42:]), 16)
+    assert rc == 0 and pcm.shape == ref.shape and (pcm == ref).all()

@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Development aid: resident encode / decode throughput for a few launch shapes (one GPU).
+
+    python tools/perf_sweep.py [--workload c2] [--seconds 600] [--threads 576,288,192] [--decode]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "flac-py_b200"), ROOT]
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+from flac import _native as N  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--seconds", type=float, default=None)
+    ap.add_argument("--threads", default="0")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--decode", action="store_true")
+    args = ap.parse_args()
+    raw, m = bench.synth(args.workload, 0, args.seconds)
+    ctx = N.Context(0)
+    n, ch, bits, bs = m["n"], m["channels"], m["bits"], m["block"]
+    cap = N.encode_bound(n, ch, bits, bs, m["rmax"])
+    d_in = ctx.device_alloc(raw.size)
+    d_out = ctx.device_alloc(cap)
+    pin = N.PinnedBuffer(raw.size)
+    pin.array[:] = raw
+    ctx.h2d(d_in, pin.ptr, raw.size)
+    enc_args = (n, ch, bits, bs, m["L"], m["q"], m["rmin"], m["rmax"], 0)
+    out_len = 0
+    for t in [int(v) for v in args.threads.split(",")]:
+        if t:
+            os.environ["FLACB200_THREADS"] = str(t)
+        else:
+            os.environ.pop("FLACB200_THREADS", None)
+        ks = []
+        for k in range(args.steps + 2):
+            rc, out_len, st = ctx.encode_raw(d_in, *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT, d_out, cap)
+            N.raise_for_status(rc)
+            if k >= 2:
+                ks.append(st.kernel_ms)
+        ms = float(np.median(ks))
+        print(json.dumps({"workload": args.workload, "threads": st.threads_per_frame, "smem": st.smem_bytes,
+                          "kernel_ms": round(ms, 4), "Msamples/s": round(n * ch / ms / 1e3, 1),
+                          "GB/s": round((raw.size + out_len) / ms / 1e6, 2), "bytes_out": out_len,
+                          "ood": int(st.out_of_domain)}), flush=True)
+    if args.decode:
+        pcm_cap = n * ch + 1024
+        d_pcm = ctx.device_alloc(pcm_cap * 4)
+        ks = []
+        for k in range(args.steps + 2):
+            rc, nsf, fch, st = ctx.decode_raw(d_out, out_len, bits, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE, d_pcm, pcm_cap)
+            N.raise_for_status(rc)
+            if k >= 2:
+                ks.append(st.kernel_ms)
+        ms = float(np.median(ks))
+        chk = np.empty(1024, dtype=np.int32)
+        ctx.d2h(chk.ctypes.data, d_pcm, 4096)
+        ok = bool((chk.reshape(-1, ch) == np.frombuffer(raw[:1024 * (bits // 8)].tobytes(), dtype="<i2" if bits == 16 else np.uint8).reshape(-1, ch)[:1024 // ch]).all()) if bits == 16 else None
+        print(json.dumps({"decode": args.workload, "kernel_ms": round(ms, 4), "frames": int(st.frames), "n_sample_frames": nsf,
+                          "false_candidates": int(st.out_of_domain), "Msamples/s": round(nsf * fch / ms / 1e3, 1),
+                          "GB/s": round((out_len + nsf * fch * bits // 8) / ms / 1e6, 2), "head_matches_input": ok}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
