@@ -88,6 +88,7 @@ struct flacb_ctx {
     HostBuf h_meta;
     int win_full_n = -1, win_tail_n = -1;
     bool win_full_ok = true, win_tail_ok = true;
+    int flat_full[2] = {0, 0}, flat_tail[2] = {0, 0};
     /* decode */
     DevBuf d_stream, d_pcm, d_cand, d_frames, d_dmisc;
     HostBuf h_dmeta;
@@ -242,11 +243,12 @@ extern "C" int flacb_sync(flacb_ctx *c)
 
 /* ------------------------------------------------------------------------------------- */
 
-static int upload_window(flacb_ctx *c, int n, DevBuf &buf, int &cached_n, bool &ok)
+static int upload_window(flacb_ctx *c, int n, DevBuf &buf, int &cached_n, bool &ok, int &flat_lo, int &flat_hi)
 {
     if (cached_n == n) return FLACB_OK;
     std::vector<double> w;
     ok = tukey_window(n, w, 64);
+    window_flat_range(w, n, flat_lo, flat_hi);
     int rc = buf.ensure(w.size() * sizeof(double));
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(buf.p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -288,8 +290,8 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     }
 
     int rc;
-    if ((rc = upload_window(c, a.block_size, c->win_full, c->win_full_n, c->win_full_ok))) return rc;
-    if ((rc = upload_window(c, tail, c->win_tail, c->win_tail_n, c->win_tail_ok))) return rc;
+    if ((rc = upload_window(c, a.block_size, c->win_full, c->win_full_n, c->win_full_ok, c->flat_full[0], c->flat_full[1]))) return rc;
+    if ((rc = upload_window(c, tail, c->win_tail, c->win_tail_n, c->win_tail_ok, c->flat_tail[0], c->flat_tail[1]))) return rc;
     if ((rc = c->frame_bytes.ensure(n_frames * 4))) return rc;
     if ((rc = c->frame_off.ensure((n_frames + 1) * 8))) return rc;
     if ((rc = c->status.ensure(n_frames * 4))) return rc;
@@ -317,6 +319,8 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     p.win_tail = (const double *)c->win_tail.p;
     p.win_full_bad = !c->win_full_ok;
     p.win_tail_bad = !c->win_tail_ok;
+    p.flat_full_lo = c->flat_full[0], p.flat_full_hi = c->flat_full[1];
+    p.flat_tail_lo = c->flat_tail[0], p.flat_tail_hi = c->flat_tail[1];
     p.frame_bytes = (uint32_t *)c->frame_bytes.p;
     p.frame_off = (u64 *)c->frame_off.p;
     p.frame_status = (int32_t *)c->status.p;
@@ -551,7 +555,7 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
     decode_frames_kernel<<<(unsigned)((n_cand + 31) / 32), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
-                                                                               d_tmpoff, d_tmp);
+                                                                               d_tmpoff, d_tmp, check_crc8);
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -561,7 +565,7 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     const u64 nsf = h_res->n_sample_frames;
     const int fch = h_res->frame_channels;
     rc = h_res->status;
-    if (rc == STATUS_CRC8_MISMATCH) return rc; /* the chain reached a frame with a bad header CRC: caller retries unfiltered */
+    if (rc == STATUS_CRC8_MISMATCH || rc == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH; /* the chain reached a frame with a bad header CRC: caller retries unfiltered */
     const u64 total = nsf * (u64)(fch > 0 ? fch : 1);
     if (total > cap_samples) {
         CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));

@@ -249,6 +249,10 @@ __device__ int parse_frame_header(BitReader &g, int si_bits, Candidate &c)
  * CRC (decoder.py:175), so such a candidate is only skipped on the fast path: if the frame chain
  * ever lands on one, the host repeats the decode without the filter. */
 constexpr int STATUS_CRC8_MISMATCH = 101;
+/* Same idea for candidates whose block size exceeds, or whose channel count differs from, the
+ * first frame's: in a fixed-block-size stream no real frame looks like that, and a garbage
+ * "frame" of 65 536 x 8 samples would keep one thread busy for tens of milliseconds. */
+constexpr int STATUS_DEFERRED = 102;
 
 __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Candidate *cand, uint32_t n_cand,
                                      uint32_t *sizes, int check_crc8)
@@ -405,12 +409,20 @@ __device__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *o
 }
 
 __global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
-                                                            const u64 *tmp_off, int32_t *tmp)
+                                                            const u64 *tmp_off, int32_t *tmp, int filter)
 {
     const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_cand) return;
     Candidate c = cand[ci];
     c.tmp_off = tmp_off[ci];
+    if (filter && ci != 0 && c.status == FLACB_OK) {
+        /* cand[0] is only read here (its thread writes it back at the very end, same values
+         * for these fields) */
+        const int bs0 = cand[0].bs, nch0 = cand[0].nch, st0 = cand[0].status;
+        const u64 start0 = cand[0].start;
+        if (start0 == 0 && (st0 == FLACB_OK || st0 == STATUS_DEFERRED) && bs0 > 0 && (c.bs > bs0 || c.nch != nch0))
+            c.status = STATUS_DEFERRED;
+    }
     if (c.status == FLACB_OK) {
         BitReader g;
         g.init(s, len, c.start);

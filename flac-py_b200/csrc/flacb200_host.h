@@ -33,6 +33,15 @@ inline bool tukey_window(int n, std::vector<double> &w, int pad)
     return true;
 }
 
+/* longest run [lo, hi) around the middle of the window whose values are exactly 1.0 */
+inline void window_flat_range(const std::vector<double> &w, int n, int &lo, int &hi)
+{
+    lo = hi = n / 2;
+    if (n <= 0 || w[(size_t)(n / 2)] != 1.0) return;
+    while (lo > 0 && w[(size_t)(lo - 1)] == 1.0) lo--;
+    while (hi < n && w[(size_t)hi] == 1.0) hi++;
+}
+
 /* crc.py:4-14 crc_table(16, 0x18005) */
 inline void crc16_table(uint16_t tab[256])
 {

@@ -80,6 +80,8 @@ struct EncParams {
     const double *win_full;    /* tukey(block_size), zero padded by 64 */
     const double *win_tail;    /* tukey(tail_size), zero padded by 64 */
     int win_full_bad, win_tail_bad; /* ZeroDivisionError of encoder.py:437 (n in 4..7) */
+    int flat_full_lo, flat_full_hi;  /* win_full[i] == 1.0 exactly for i in [lo, hi) */
+    int flat_tail_lo, flat_tail_hi;
     uint8_t *out;
     u64 out_cap;
     u64 slot_stride;           /* != 0: slot mode (frame f at f * slot_stride) */
@@ -150,6 +152,7 @@ struct Decision {
 
 struct Shared {
     double autoc[FLACB_MAX_LPC + 1];
+    i64 isum[FLACB_MAX_LPC + 1]; /* exact integer part of the autocorrelation */
     double ldc[FLACB_MAX_LPC][FLACB_MAX_LPC]; /* Levinson coefficients after iteration k */
     int32_t qc[FLACB_MAX_LPC][FLACB_MAX_LPC];
     int32_t qshift[FLACB_MAX_LPC], qncoef[FLACB_MAX_LPC], qstat[FLACB_MAX_LPC];
@@ -190,6 +193,7 @@ struct Blk {
     uint32_t *pst;
     u64 *red;
     const double *win;
+    int flat_lo, flat_hi;
     __device__ Blk(const EncParams &p_, Shared &sh_) : p(p_), sh(sh_) {}
 };
 
@@ -202,14 +206,28 @@ __device__ __forceinline__ void set_status(Blk &b, int code)
 /* ------------------------------------------------------------------------------------- */
 /* block-wide primitives                                                                  */
 
+/* warp sums through the integer reduction unit (REDUX): three 21-bit pieces, each of which
+ * sums to less than 2^26 over 32 lanes.  Exact for |v| < 2^62. */
+__device__ __forceinline__ u64 warp_sum_u64(u64 v)
+{
+    const uint32_t p0 = (uint32_t)v & 0x1FFFFFu, p1 = (uint32_t)(v >> 21) & 0x1FFFFFu, p2 = (uint32_t)(v >> 42);
+    return (u64)__reduce_add_sync(FULL, p0) + ((u64)__reduce_add_sync(FULL, p1) << 21) +
+           ((u64)__reduce_add_sync(FULL, p2) << 42);
+}
+
+__device__ __forceinline__ i64 warp_sum_i64(i64 v)
+{
+    const uint32_t p0 = (uint32_t)v & 0x1FFFFFu, p1 = (uint32_t)(v >> 21) & 0x1FFFFFu;
+    const int p2 = (int)(v >> 42); /* arithmetic: v = p2 * 2^42 + p1 * 2^21 + p0 */
+    return (i64)__reduce_add_sync(FULL, p0) + ((i64)__reduce_add_sync(FULL, p1) << 21) +
+           (i64)__reduce_add_sync(FULL, p2) * ((i64)1 << 42);
+}
+
 template <int K>
 __device__ void block_reduce_u64(Blk &b, u64 (&v)[K], u64 *out)
 {
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], off);
-    }
+    for (int k = 0; k < K; k++) v[k] = warp_sum_u64(v[k]);
     if (b.lane == 0) {
 #pragma unroll
         for (int k = 0; k < K; k++) b.red[b.warp * K + k] = v[k];
@@ -386,10 +404,55 @@ __device__ __forceinline__ void dd_add(double &s, double &c, double x)
     c = __dadd_rn(c, err);
 }
 
-template <int LG>
+/* A thread's 8 samples are "flat" when every window value they touch (up to lag L ahead) is
+ * exactly 1.0 and no product is cut off at the end of the block: then w = x, the products are
+ * integers below 2^53 and their sum is exact in int64.  Half of a Tukey(0.5) window is flat. */
+__device__ __forceinline__ bool autoc_flat(const Blk &b, int i0, int L)
+{
+    return i0 >= b.flat_lo && i0 + E - 1 + L < b.flat_hi && i0 + E - 1 < b.n - L - 1;
+}
+
+template <int LG, int LGI>
 __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
 {
     const int n = b.n;
+    if (b.tid <= FLACB_MAX_LPC) b.sh.isum[b.tid] = 0;
+    __syncthreads();
+    /* ---- integer part ---- */
+    for (int lag0 = 0; lag0 <= L; lag0 += LGI) {
+        i64 acc[LGI];
+#pragma unroll
+        for (int l = 0; l < LGI; l++) acc[l] = 0;
+        bool any = false;
+        for (int tile = 0; tile < b.ntiles; tile++) {
+            const int i0 = (tile * b.B + b.tid) * E;
+            if (i0 < n && autoc_flat(b, i0, L)) {
+                any = true;
+                int xa[E], xb[E + LGI - 1];
+#pragma unroll
+                for (int e = 0; e < E; e++) xa[e] = x[padidx((uint32_t)(GUARD + i0 + e))];
+#pragma unroll
+                for (int j = 0; j < E + LGI - 1; j++) xb[j] = x[padidx((uint32_t)(GUARD + i0 + lag0 + j))];
+#pragma unroll
+                for (int l = 0; l < LGI; l++) {
+                    if (lag0 + l <= L) {
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[l] += (i64)xa[e] * (i64)xb[e + l];
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, any)) { /* warp-uniform */
+#pragma unroll
+            for (int l = 0; l < LGI; l++) {
+                if (lag0 + l <= L) {
+                    const i64 t = warp_sum_i64(acc[l]);
+                    if (b.lane == 0 && t) atomicAdd((u64 *)&b.sh.isum[lag0 + l], (u64)t);
+                }
+            }
+        }
+    }
+    /* ---- windowed part, double-double ---- */
     double2 *redd = (double2 *)b.red;
     for (int lag0 = 0; lag0 <= L; lag0 += LG) {
         double s[LG], c[LG];
@@ -397,7 +460,7 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
         for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
         for (int tile = 0; tile < b.ntiles; tile++) {
             const int i0 = (tile * b.B + b.tid) * E;
-            if (i0 < n) {
+            if (i0 < n && !autoc_flat(b, i0, L)) {
                 double wa[E], wb[E + LG - 1];
 #pragma unroll
                 for (int e = 0; e < E; e++)
@@ -442,6 +505,11 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                 dd_add(S, C, v.x);
                 C = __dadd_rn(C, v.y);
             }
+            /* the exact integer part, split into two doubles that each hold it exactly */
+            const i64 iv = b.sh.isum[lag0 + b.tid];
+            const i64 hi = iv & ~(i64)0x7FF, lo = iv & (i64)0x7FF;
+            dd_add(S, C, (double)hi);
+            dd_add(S, C, (double)lo);
             b.sh.autoc[lag0 + b.tid] = __dadd_rn(S, C);
         }
         __syncthreads();
@@ -549,6 +617,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 #pragma unroll
             for (int j = 0; j < LMAX + E; j++) h[j] = 0;
         }
+        const bool interior = i0 >= LMAX && i0 + E <= n; /* no warm-up or end-of-block masking */
 #pragma unroll
         for (int m = 1; m <= LMAX; m++) {
             if (m <= L && sh.qncoef[m - 1] != 0) {
@@ -564,12 +633,22 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 #pragma unroll
                         for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
                     }
+                    if (interior) {
+                        /* |r| < 2^31 each: pairs fit 32 bits */
 #pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        const int i = i0 + e;
-                        if (i >= m && i < n) {
-                            const int r = h[LMAX + e] - (acc[e] >> shift);
-                            tot += (u64)(uint32_t)(r < 0 ? -r : r);
+                        for (int e = 0; e < E; e += 2) {
+                            const int r0 = h[LMAX + e] - (acc[e] >> shift);
+                            const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
+                            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const int i = i0 + e;
+                            if (i >= m && i < n) {
+                                const int r = h[LMAX + e] - (acc[e] >> shift);
+                                tot += (u64)(uint32_t)(r < 0 ? -r : r);
+                            }
                         }
                     }
                 } else {
@@ -591,8 +670,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
                         }
                     }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                tot = warp_sum_u64(tot);
                 if (b.lane == 0 && tot) atomicAdd(&sh.lpc_err[m - 1], tot);
             }
         }
@@ -790,7 +868,14 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
             }
         }
     }
-    block_reduce_u64<MAX_CAND>(b, acc, sh.qsum);
+#pragma unroll
+    for (int ci = 0; ci < MAX_CAND; ci++) {
+        if (ci < ncand) {
+            const u64 t = warp_sum_u64(acc[ci]);
+            if (b.lane == 0 && t) atomicAdd(&sh.qsum[ci], t);
+        }
+    }
+    __syncthreads();
     if (b.tid == 0) {
         int best = 0;
         u64 best_size = 0;
@@ -1076,7 +1161,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
         if (bad_win) {
             if (b.tid == 0) set_status(b, FLACB_E_ZERODIV); /* encoder.py:437 */
         } else {
-            autocorrelation<4>(b, x, L);
+            autocorrelation<4, (LMAX <= 12 ? 13 : 11)>(b, x, L);
             if (b.tid == 0) levinson(b, L);
             __syncthreads();
             if (sh.lev_stat == 0) {
@@ -1196,7 +1281,10 @@ __global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams 
     const uint32_t f = sh.frame;
     b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
     b.ntiles = (b.n + b.B * E - 1) / (b.B * E);
-    b.win = (f == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail : p.win_full;
+    const bool tail_frame = f == p.n_frames - 1 && p.tail_size != p.block_size;
+    b.win = tail_frame ? p.win_tail : p.win_full;
+    b.flat_lo = tail_frame ? p.flat_tail_lo : p.flat_full_lo;
+    b.flat_hi = tail_frame ? p.flat_tail_hi : p.flat_full_hi;
 
     const SmemLayout lay = make_layout(p.block_size, p.channels, p.rmax, p.smem_limit);
     b.xs = (int32_t *)(smem + lay.xs);

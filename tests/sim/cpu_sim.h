@@ -192,6 +192,17 @@ static inline unsigned __ballot_sync(unsigned, int pred)
     return r;
 }
 
+template <class T> static inline T __reduce_add_sync(unsigned, T v)
+{
+    sim::State &s = sim::st();
+    const int w = s.cur >> 5, lane = s.cur & 31;
+    s.wbuf[w][lane] = (unsigned long long)(long long)v;
+    sim::syncwarp();
+    T r = 0;
+    for (int l = 0; l < 32; l++) r = (T)(r + (T)(long long)s.wbuf[w][l]);
+    sim::syncwarp();
+    return r;
+}
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __clzll(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -63,6 +63,8 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     p.win_tail_bad = !tukey_window(p.tail_size, wt, 64);
     p.win_full = wf.data();
     p.win_tail = wt.data();
+    window_flat_range(wf, block_size, p.flat_full_lo, p.flat_full_hi);
+    window_flat_range(wt, p.tail_size, p.flat_tail_lo, p.flat_tail_hi);
     p.smem_limit = smem_limit;
 
     const SmemLayout lay = make_layout(block_size, channels, rice_max, smem_limit);
@@ -172,10 +174,10 @@ static int sim_decode_impl(const uint8_t *frames, uint64_t len, int streaminfo_b
     sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
     std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
     for (unsigned b = 0; b < nb; b++)
-        sim::run_block(b, nb, 128, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data()); });
+        sim::run_block(b, nb, 128, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8); });
     DecodeResult res;
     sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
-    if (res.status == STATUS_CRC8_MISMATCH) return res.status;
+    if (res.status == STATUS_CRC8_MISMATCH || res.status == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH;
     const u64 total = res.n_sample_frames * (u64)(res.frame_channels > 0 ? res.frame_channels : 1);
     if (total > cap_samples) return FLACB_E_NOSPACE;
     if (total)

@@ -121,3 +121,13 @@ def test_decode_ignores_crcs_like_the_reference():
     ref = O.decode_stream(bytes(stream))[4]
     pcm, fch = decode_frames(bytes(stream[42:]), 16)
     assert pcm.shape == ref.shape and (pcm == ref).all()
+
+
+def test_decode_variable_block_sizes():
+    """frames larger than frame 0's: the fast path defers them, the unfiltered repeat decodes them"""
+    from flac.decoder import decode_frames
+    a = S.pcm(1000 * 2, 2, 16, 44100, "white", 21)
+    b = S.pcm(4096 + 500, 2, 16, 44100, "sine", 22)
+    frames = O.encode_frames(a, 16, 1000, 8, 6, 0, 3).data + O.encode_frames(b, 16, 4096, 8, 6, 0, 3).data
+    pcm, fch = decode_frames(frames, 16)
+    assert fch == 2 and (pcm == np.concatenate([a, b])).all()

@@ -122,3 +122,19 @@ def test_sim_decode_ignores_crcs_like_the_reference():
     ref = O.decode_stream(bytes(stream))[4]
     rc, pcm, fch, _ = simlib.decode_frames(bytes(stream[42:]), 16)
     assert rc == 0 and pcm.shape == ref.shape and (pcm == ref).all()
+
+
+def test_sim_decode_variable_block_sizes_take_the_unfiltered_path():
+    """frames larger than frame 0's are deferred by the fast path; the decode then repeats
+    unfiltered and matches the serial decoder"""
+    import flacb200_synth as S
+    a = S.pcm(1000 * 2, 2, 16, 44100, "white", 21)
+    b = S.pcm(4096 + 500, 2, 16, 44100, "sine", 22)
+    ea = O.encode_frames(a, 16, 1000, 8, 6, 0, 3)
+    eb = O.encode_frames(b, 16, 4096, 8, 6, 0, 3)
+    frames = ea.data + eb.data
+    stream = O.stream_prologue(44100, 2, 16, a.shape[0] + b.shape[0], 4096) + frames
+    ref = O.decode_stream(stream)[4]
+    rc, pcm, fch, _ = simlib.decode_frames(frames, 16)
+    assert rc == 0 and pcm.shape == ref.shape and (pcm == ref).all()
+    assert (pcm == np.concatenate([a, b])).all()
