@@ -141,9 +141,9 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     CUDA_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<12>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1>));
     c->static_smem12 = fa.sharedSizeBytes;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<32>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<32, 576, 1>));
     c->static_smem32 = fa.sharedSizeBytes;
     /* CRC-16 tables (crc.py:4-14) and the x^n weights of the parallel CRC */
     uint16_t tab[256], lo[256];
@@ -275,19 +275,20 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     const bool lmax12 = a.max_lpc_order <= 12;
     const size_t static_smem = lmax12 ? c->static_smem12 : c->static_smem32;
     if ((size_t)c->smem_optin <= static_smem + 1024) return FLACB_E_UNSUPPORTED;
-    const uint32_t smem_limit = (uint32_t)((size_t)c->smem_optin - static_smem);
-    const SmemLayout lay = make_layout(a.block_size, a.channels, a.rice_max, smem_limit);
-    if (lay.total > smem_limit) return FLACB_E_UNSUPPORTED;
     if (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) >= (u64)XPOW_HI * 256) return FLACB_E_UNSUPPORTED;
-    /* two CTAs per SM whenever shared memory allows it: the kernel is latency bound (serial
-     * Levinson, barriers), a second resident frame hides that (measured: profiles/) */
-    const size_t per_sm = 228 * 1024;
-    const bool two_per_sm = 2 * ((size_t)lay.total + static_smem + 1024) <= per_sm;
-    int B = pick_threads(a.block_size, E, two_per_sm ? MAXB / 2 : MAXB);
-    if (const char *e = getenv("FLACB200_THREADS")) { /* tuning knob: threads per frame */
-        const int v = atoi(e);
-        if (v >= 32 && v <= MAXB && v % 32 == 0) B = v;
+    auto layout_total = [&](int threads, int all_planes) {
+        return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
+    };
+    LaunchShape shape = pick_shape(a.block_size, E, static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total);
+    if (shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
+    if (const char *e = getenv("FLACB200_SHAPE")) { /* tuning knob: "threads,all_planes,variant" */
+        int t = 0, ap = 1, v = 0;
+        if (sscanf(e, "%d,%d,%d", &t, &ap, &v) == 3 && t >= 32 && t % 32 == 0 && t <= (v ? 288 : 576) &&
+            layout_total(t, ap) + static_smem <= (size_t)c->smem_optin)
+            shape.threads = t, shape.all_planes = ap, shape.variant = v;
     }
+    const int B = shape.threads;
+    const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, shape.all_planes);
 
     int rc;
     if ((rc = upload_window(c, a.block_size, c->win_full, c->win_full_n, c->win_full_ok, c->flat_full[0], c->flat_full[1]))) return rc;
@@ -328,7 +329,7 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     p.ticket = (uint32_t *)c->misc.p;
     p.stats = (u64 *)((uint8_t *)c->misc.p + 64);
     p.info = d_info;
-    p.smem_limit = smem_limit;
+    p.all_planes = shape.all_planes;
     if (a.flags & FLACB_SLOT_COMPACT) {
         p.slot_stride = (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) + 15) & ~15ull;
         if ((rc = c->slots.ensure(p.slot_stride * n_frames))) return rc;
@@ -343,13 +344,17 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 128, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->lb.p, 0, n_frames * 8, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_k0, c->stream));
-    if (lmax12) {
-        CUDA_TRY(cudaFuncSetAttribute(encode_frames_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-        encode_frames_kernel<12><<<(unsigned)n_frames, B, lay.total, c->stream>>>(p);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(encode_frames_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-        encode_frames_kernel<32><<<(unsigned)n_frames, B, lay.total, c->stream>>>(p);
-    }
+#define FLACB_LAUNCH(LM, TB, MB)                                                                                   \
+    do {                                                                                                           \
+        CUDA_TRY(cudaFuncSetAttribute(encode_frames_kernel<LM, TB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)lay.total));                                                            \
+        encode_frames_kernel<LM, TB, MB><<<(unsigned)n_frames, B, lay.total, c->stream>>>(p);                     \
+    } while (0)
+    if (lmax12 && shape.variant) FLACB_LAUNCH(12, 288, 3);
+    else if (lmax12) FLACB_LAUNCH(12, 576, 1);
+    else if (shape.variant) FLACB_LAUNCH(32, 288, 3);
+    else FLACB_LAUNCH(32, 576, 1);
+#undef FLACB_LAUNCH
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (a.flags & FLACB_SLOT_COMPACT) {
@@ -554,7 +559,7 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     if ((rc = c->d_frames.ensure((tmp_samples + 16) * 4))) return rc;
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
-    decode_frames_kernel<<<(unsigned)((n_cand + 31) / 32), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
+    decode_frames_kernel<<<(unsigned)((n_cand + DECODE_WARPS - 1) / DECODE_WARPS), 32 * DECODE_WARPS, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
                                                                                d_tmpoff, d_tmp, check_crc8);
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;

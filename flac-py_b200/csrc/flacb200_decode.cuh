@@ -137,9 +137,21 @@ struct BitReader {
     }
     __device__ __forceinline__ void refill()
     {
-        while (avail <= 56 && next < len) {
-            buf |= (u64)p[next++] << (56 - avail);
-            avail += 8;
+        /* aligned 32-bit loads while a whole word is left (keeps 33..64 bits buffered), single
+         * bytes in front of the first aligned word and behind the last one */
+        for (;;) {
+            if (next >= len) return;
+            if (next + 4 <= len && (((uintptr_t)(p + next)) & 3) == 0) {
+                if (avail > 32) return;
+                const uint32_t w = *(const uint32_t *)(p + next);
+                buf |= (u64)__byte_perm(w, 0, 0x0123) << (32 - avail); /* the stream is big endian */
+                avail += 32;
+                next += 4;
+            } else {
+                if (avail > 56) return;
+                buf |= (u64)p[next++] << (56 - avail);
+                avail += 8;
+            }
         }
     }
     /* n in 0..32 */
@@ -408,11 +420,18 @@ __device__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *o
     return FLACB_OK;
 }
 
-__global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
-                                                            const u64 *tmp_off, int32_t *tmp, int filter)
+/* One WARP per candidate, lane 0 does the work: Rice parsing is a serial, data dependent walk
+ * through the bit stream, and 32 lanes walking 32 different frames diverge at every code (the
+ * first version did that and ran 30x slower).  Parallelism comes from the frames: thousands of
+ * independent warps, one per SM sub-partition slot. */
+constexpr int DECODE_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * DECODE_WARPS) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand,
+                                                                         uint32_t n_cand, const u64 *tmp_off,
+                                                                         int32_t *tmp, int filter)
 {
-    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= n_cand) return;
+    const uint32_t ci = blockIdx.x * DECODE_WARPS + (threadIdx.x >> 5);
+    if (ci >= n_cand || (threadIdx.x & 31) != 0) return;
     Candidate c = cand[ci];
     c.tmp_off = tmp_off[ci];
     if (filter && ci != 0 && c.status == FLACB_OK) {

@@ -133,6 +133,41 @@ inline int pick_threads(int block_size, int e, int maxb)
     return b;
 }
 
+/* Launch shape: how many threads per frame, whether every channel plane stays in shared memory,
+ * and how many frames share an SM.  The kernel is latency bound (barriers, serial Levinson
+ * recursion), so resident frames per SM come first: up to 3 with the <288, 3> instantiation
+ * (72 registers), then threads per frame. */
+struct LaunchShape {
+    int threads, all_planes, ctas_per_sm, variant; /* variant 0: <576,1>, 1: <288,3> */
+};
+
+template <class LayoutFn>
+inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t smem_optin, size_t smem_per_sm,
+                              LayoutFn layout_total)
+{
+    LaunchShape best = {0, 0, 0, 0};
+    for (int variant = 1; variant >= 0; variant--) {
+        const int maxb = variant ? 288 : 576;
+        const int regs = variant ? 72 : 96;
+        for (int all_planes = 1; all_planes >= 0; all_planes--) {
+            const int threads = pick_threads(block_size, e, maxb);
+            const size_t dyn = layout_total(threads, all_planes);
+            if (dyn + static_smem > smem_optin) continue;
+            int by_smem = (int)(smem_per_sm / (dyn + static_smem + 1024));
+            int by_regs = 65536 / (regs * threads);
+            int ctas = by_smem < by_regs ? by_smem : by_regs;
+            if (variant && ctas > 3) ctas = 3;
+            if (!variant && ctas > 2) ctas = 2;
+            if (ctas < 1) continue;
+            /* more resident warps first, then resident planes (no reload) */
+            const int score = ctas * threads * 4 + all_planes;
+            const int best_score = best.ctas_per_sm * best.threads * 4 + best.all_planes;
+            if (best.threads == 0 || score > best_score) best = {threads, all_planes, ctas, variant};
+        }
+    }
+    return best;
+}
+
 /* encoder.py:61-83, :170-189: magic, metadata block header (last, STREAMINFO, 34), STREAMINFO
  * with min = max block size, frame sizes 0, and a zero MD5 */
 inline void stream_prologue(uint32_t sample_rate, int channels, int bits, uint64_t total_samples,

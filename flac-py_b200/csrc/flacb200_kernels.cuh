@@ -54,6 +54,7 @@ constexpr int TAILPAD = 48;     /* zero samples behind a plane (window reads run
 constexpr int STG_WORDS = FLACB_STG_WORDS; /* staging window of the bit packer, 32-bit words */
 constexpr int MAXB = 576;       /* threads per CTA, upper bound */
 constexpr int MAX_CH = 8;
+constexpr int RED_STRIDE = 40;  /* u64 slots per warp in the reduction scratch */
 constexpr int MAX_CAND = 16;    /* Rice partition orders 0..15 */
 constexpr int CRC_SLICE = 64;   /* bytes per thread in the parallel CRC-16 */
 constexpr int XPOW_HI = 8192;   /* x^(8*256*h) table entries: frames up to 2 MiB */
@@ -92,43 +93,45 @@ struct EncParams {
     uint32_t *ticket;          /* zeroed before launch */
     u64 *stats;                /* device counters: [0..4] fixed order histogram, [5] lpc, [6] ood */
     flacb_subframe_info *info; /* optional, device memory */
-    uint32_t smem_limit;
+    int all_planes;            /* every channel plane resident in shared memory */
 };
 
 struct SmemLayout {
-    uint32_t xs, xwords, res, cum, kall, stg, fb, pst, red, total;
+    uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, ldc, qc, total;
     int xs_all;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-/* Shared memory plan for a block size / channel count.  xs_all = every channel plane resident;
- * otherwise one plane that is (re)loaded per channel and phase. */
-__host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int rmax, uint32_t limit)
+/* Shared memory plan.  all_planes: every channel plane resident; otherwise one plane that is
+ * (re)loaded per channel and phase, which leaves room for more CTAs per SM.  `threads` sizes the
+ * staging window: a tile of threads * E samples packs into at most (bps + 4) bits per sample
+ * (SURVEY.md 9.5), so a window of that size never needs a second pass. */
+__host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bps, int rmax, int L, int threads,
+                                                   int all_planes)
 {
     SmemLayout l;
     l.xwords = padidx((uint32_t)(GUARD + nmax + TAILPAD)) + 1;
-    uint32_t rest = 0;
-    uint32_t res_b = align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
-    uint32_t cum_b = align16(((uint32_t)nmax / E + 4) * 8);
-    uint32_t kall_b = align16(2u << rmax);
-    uint32_t stg_b = align16((STG_WORDS + 4) * 4);
-    uint32_t fb_b = align16(MAXB * 4);
-    uint32_t pst_b = align16((MAXB + 1) * 4);
-    uint32_t red_b = align16((MAXB / 32) * 32 * 8);
-    rest = res_b + cum_b + kall_b + stg_b + fb_b + pst_b + red_b;
-    uint32_t plane = align16(l.xwords * 4);
-    l.xs_all = ((u64)plane * (u64)channels + rest <= limit) ? 1 : 0;
+    const uint32_t plane = align16(l.xwords * 4);
+    int tile = threads * E < nmax ? threads * E : nmax;
+    uint32_t words = ((uint32_t)tile * (uint32_t)(bps + 4) + 31) / 32 + 96; /* + serial header part */
+    if (words < 512) words = 512;
+    if (words > (uint32_t)STG_WORDS) words = (uint32_t)STG_WORDS;
+    l.stg_words = words;
+    l.xs_all = all_planes;
     uint32_t off = 0;
-    l.xs = off;
-    off += l.xs_all ? plane * (uint32_t)channels : plane;
-    l.res = off; off += res_b;
-    l.cum = off; off += cum_b;
-    l.kall = off; off += kall_b;
-    l.stg = off; off += stg_b;
-    l.fb = off; off += fb_b;
-    l.pst = off; off += pst_b;
-    l.red = off; off += red_b;
+    l.xs = off; off += all_planes ? plane * (uint32_t)channels : plane;
+    l.res = off; off += align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
+    l.cum = off; off += align16(((uint32_t)nmax / E + 4) * 8);
+    l.kall = off; off += align16(2u << rmax);
+    l.stg = off; off += align16((words + 4) * 4);
+    /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
+    uint32_t red_b = align16((MAXB / 32) * RED_STRIDE * 8);
+    const uint32_t pack_b = align16(MAXB * 4) + align16((MAXB + 1) * 4);
+    if (red_b < pack_b) red_b = pack_b;
+    l.red = off; l.fb = off; l.pst = off + align16(MAXB * 4); off += red_b;
+    l.ldc = off; off += align16((uint32_t)(L * L) * 8);
+    l.qc = off; off += align16((uint32_t)(L * L) * 4);
     l.total = off;
     return l;
 }
@@ -153,8 +156,6 @@ struct Decision {
 struct Shared {
     double autoc[FLACB_MAX_LPC + 1];
     i64 isum[FLACB_MAX_LPC + 1]; /* exact integer part of the autocorrelation */
-    double ldc[FLACB_MAX_LPC][FLACB_MAX_LPC]; /* Levinson coefficients after iteration k */
-    int32_t qc[FLACB_MAX_LPC][FLACB_MAX_LPC];
     int32_t qshift[FLACB_MAX_LPC], qncoef[FLACB_MAX_LPC], qstat[FLACB_MAX_LPC];
     uint32_t qabs[FLACB_MAX_LPC];
     u64 lpc_err[FLACB_MAX_LPC];
@@ -192,6 +193,10 @@ struct Blk {
     uint32_t *fb;
     uint32_t *pst;
     u64 *red;
+    double *ldc;   /* [L][L] Levinson coefficients after iteration k */
+    int32_t *qc;   /* [L][L] quantised coefficients per order */
+    int ldL;       /* row stride of ldc / qc */
+    uint32_t stg_words;
     const double *win;
     int flat_lo, flat_hi;
     __device__ Blk(const EncParams &p_, Shared &sh_) : p(p_), sh(sh_) {}
@@ -210,6 +215,11 @@ __device__ __forceinline__ void set_status(Blk &b, int code)
  * sums to less than 2^26 over 32 lanes.  Exact for |v| < 2^62. */
 __device__ __forceinline__ u64 warp_sum_u64(u64 v)
 {
+#ifdef FLACB_WARPSUM_SHFL
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+#endif
     const uint32_t p0 = (uint32_t)v & 0x1FFFFFu, p1 = (uint32_t)(v >> 21) & 0x1FFFFFu, p2 = (uint32_t)(v >> 42);
     return (u64)__reduce_add_sync(FULL, p0) + ((u64)__reduce_add_sync(FULL, p1) << 21) +
            ((u64)__reduce_add_sync(FULL, p2) << 42);
@@ -217,6 +227,11 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v)
 
 __device__ __forceinline__ i64 warp_sum_i64(i64 v)
 {
+#ifdef FLACB_WARPSUM_SHFL
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+#endif
     const uint32_t p0 = (uint32_t)v & 0x1FFFFFu, p1 = (uint32_t)(v >> 21) & 0x1FFFFFu;
     const int p2 = (int)(v >> 42); /* arithmetic: v = p2 * 2^42 + p1 * 2^21 + p0 */
     return (i64)__reduce_add_sync(FULL, p0) + ((i64)__reduce_add_sync(FULL, p1) << 21) +
@@ -416,8 +431,6 @@ template <int LG, int LGI>
 __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
 {
     const int n = b.n;
-    if (b.tid <= FLACB_MAX_LPC) b.sh.isum[b.tid] = 0;
-    __syncthreads();
     /* ---- integer part ---- */
     for (int lag0 = 0; lag0 <= L; lag0 += LGI) {
         i64 acc[LGI];
@@ -442,16 +455,22 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                 }
             }
         }
-        if (__ballot_sync(FULL, any)) { /* warp-uniform */
+        const bool warp_any = __ballot_sync(FULL, any) != 0; /* warp-uniform */
 #pragma unroll
-            for (int l = 0; l < LGI; l++) {
-                if (lag0 + l <= L) {
-                    const i64 t = warp_sum_i64(acc[l]);
-                    if (b.lane == 0 && t) atomicAdd((u64 *)&b.sh.isum[lag0 + l], (u64)t);
-                }
+        for (int l = 0; l < LGI; l++) {
+            if (lag0 + l <= L) {
+                const i64 t = warp_any ? warp_sum_i64(acc[l]) : 0;
+                if (b.lane == 0) b.red[b.warp * RED_STRIDE + lag0 + l] = (u64)t; /* one writer per slot */
             }
         }
     }
+    __syncthreads();
+    if (b.tid <= L) {
+        u64 t = 0;
+        for (int w = 0; w < b.nwarps; w++) t += b.red[w * RED_STRIDE + b.tid];
+        b.sh.isum[b.tid] = (i64)t;
+    }
+    __syncthreads();
     /* ---- windowed part, double-double ---- */
     double2 *redd = (double2 *)b.red;
     for (int lag0 = 0; lag0 <= L; lag0 += LG) {
@@ -549,7 +568,7 @@ __device__ void levinson(Blk &b, int L)
         if (isinf(l2) && !isinf(lambda)) { stat = FLACB_E_OVERFLOW; break; }
         error = __dmul_rn(error, __dsub_rn(1.0, l2));
 #pragma unroll 1
-        for (int j = 0; j <= k; j++) sh.ldc[k][j] = coefs[j + 1];
+        for (int j = 0; j <= k; j++) b.ldc[k * b.ldL + j] = coefs[j + 1];
     }
     sh.lev_stat = stat;
 }
@@ -558,7 +577,7 @@ __device__ void levinson(Blk &b, int L)
 __device__ void quantize_order(Blk &b, int m, int precision)
 {
     Shared &sh = b.sh;
-    const double *c = sh.ldc[m - 1];
+    const double *c = b.ldc + (m - 1) * b.ldL;
     double cmax = 0.0;
     bool any_nan = false;
     for (int i = 0; i < m; i++) {
@@ -586,7 +605,7 @@ __device__ void quantize_order(Blk &b, int m, int precision)
         const double r = rint(error); /* round(): half to even */
         const i64 qi = r < (double)qmin ? qmin : (r > (double)qmax ? qmax : (i64)r);
         error = __dsub_rn(error, (double)qi);
-        sh.qc[m - 1][i] = (int32_t)qi;
+        b.qc[(m - 1) * b.ldL + i] = (int32_t)qi;
         asum += (uint32_t)(qi < 0 ? -qi : qi);
     }
     sh.qncoef[m - 1] = m;
@@ -604,9 +623,8 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 {
     Shared &sh = b.sh;
     const int n = b.n;
-    if (b.tid < FLACB_MAX_LPC) sh.lpc_err[b.tid] = 0;
-    __syncthreads();
     const u64 lim32 = 1ull << 30;
+    u64 lane_tot = 0; /* lane m-1 of every warp keeps the warp's running total of order m */
     for (int tile = 0; tile < b.ntiles; tile++) {
         const int i0 = (tile * b.B + b.tid) * E;
         int h[LMAX + E];
@@ -629,7 +647,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
                     for (int e = 0; e < E; e++) acc[e] = 0;
 #pragma unroll
                     for (int j = 0; j < m; j++) {
-                        const int cj = sh.qc[m - 1][j];
+                        const int cj = b.qc[(m - 1) * b.ldL + j];
 #pragma unroll
                         for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
                     }
@@ -657,7 +675,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
                     for (int e = 0; e < E; e++) acc[e] = 0;
 #pragma unroll
                     for (int j = 0; j < m; j++) {
-                        const i64 cj = sh.qc[m - 1][j];
+                        const i64 cj = b.qc[(m - 1) * b.ldL + j];
 #pragma unroll
                         for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
                     }
@@ -671,9 +689,16 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
                     }
                 }
                 tot = warp_sum_u64(tot);
-                if (b.lane == 0 && tot) atomicAdd(&sh.lpc_err[m - 1], tot);
+                if (b.lane == m - 1) lane_tot += tot;
             }
         }
+    }
+    b.red[b.warp * RED_STRIDE + b.lane] = lane_tot;
+    __syncthreads();
+    if (b.tid < L) {
+        u64 t = 0;
+        for (int w = 0; w < b.nwarps; w++) t += b.red[w * RED_STRIDE + b.tid];
+        sh.lpc_err[b.tid] = t;
     }
     __syncthreads();
 }
@@ -868,12 +893,20 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
             }
         }
     }
+    u64 lane_q = 0;
 #pragma unroll
     for (int ci = 0; ci < MAX_CAND; ci++) {
         if (ci < ncand) {
             const u64 t = warp_sum_u64(acc[ci]);
-            if (b.lane == 0 && t) atomicAdd(&sh.qsum[ci], t);
+            if (b.lane == ci) lane_q = t;
         }
+    }
+    if (b.lane < MAX_CAND) b.red[b.warp * RED_STRIDE + b.lane] = lane_q;
+    __syncthreads();
+    if (b.tid < ncand) {
+        u64 t = 0;
+        for (int w = 0; w < b.nwarps; w++) t += b.red[w * RED_STRIDE + b.tid];
+        sh.qsum[b.tid] = t;
     }
     __syncthreads();
     if (b.tid == 0) {
@@ -949,9 +982,9 @@ __device__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
         atomicXor(&sh.crc, gf16_mul(c, w));
     }
     const uint32_t carry_idx = wend - sh.wbase;
-    const uint32_t carry = carry_idx <= STG_WORDS ? b.stg[carry_idx] : 0u;
+    const uint32_t carry = carry_idx <= b.stg_words ? b.stg[carry_idx] : 0u;
     __syncthreads();
-    for (int idx = b.tid; idx < STG_WORDS + 4; idx += b.B) b.stg[idx] = idx == 0 ? carry : 0u;
+    for (int idx = b.tid; idx < (int)b.stg_words + 4; idx += b.B) b.stg[idx] = idx == 0 ? carry : 0u;
     if (b.tid == 0) sh.wbase = wend;
     __syncthreads();
 }
@@ -1032,7 +1065,7 @@ __device__ void pack_residual(Blk &b, const Decision &d)
         b.pst[b.tid] = sh.pos + ex;
         if (tile_bits == 0) continue; /* uniform */
         const uint32_t tile_end = sh.pos + tile_bits;
-        if ((tile_end >> 5) >= sh.wbase + STG_WORDS) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
+        if ((tile_end >> 5) >= sh.wbase + b.stg_words) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
         else __syncthreads();
         const uint32_t p_start = sh.pos + ex;
         const uint32_t p_end = p_start + nbits;
@@ -1040,7 +1073,7 @@ __device__ void pack_residual(Blk &b, const Decision &d)
             Packer pk;
             pk.stg = b.stg;
             pk.win_lo = sh.wbase;
-            pk.win_hi = sh.wbase + STG_WORDS;
+            pk.win_hi = sh.wbase + b.stg_words;
             pk.acc = 0;
             pk.w = p_start >> 5;
             pk.f_w = p_start >> 5;
@@ -1083,8 +1116,8 @@ __device__ void pack_residual(Blk &b, const Decision &d)
                 else b.stg[pk.l_w - pk.win_lo] = v;
             }
             __syncthreads();
-            if ((tile_end >> 5) < sh.wbase + STG_WORDS) break;
-            flush_window(b, STG_WORDS * 4u, sh.wbase + STG_WORDS);
+            if ((tile_end >> 5) < sh.wbase + b.stg_words) break;
+            flush_window(b, b.stg_words * 4u, sh.wbase + b.stg_words);
         }
         if (b.tid == 0) sh.pos = tile_end;
         __syncthreads();
@@ -1214,7 +1247,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
         d.shift = use_lpc ? sh.qshift[lo - 1] : 0;
         d.ncoef = use_lpc ? lo : 0;
         if (use_lpc)
-            for (int j = 0; j < lo; j++) d.q[j] = sh.qc[lo - 1][j];
+            for (int j = 0; j < lo; j++) d.q[j] = b.qc[(lo - 1) * b.ldL + j];
         if (use_lpc && p.P - 1 == 15) set_status(b, FLACB_E_ASSERT); /* encoder.py:619 */
         if (inf) {
             inf->type = d.type;
@@ -1229,7 +1262,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
                 inf->lpc_err[m] = have ? (int64_t)(sh.qncoef[m] ? sh.lpc_err[m] : sh.fixed_err[0]) : 0;
                 inf->lpc_shift[m] = have ? sh.qshift[m] : 0;
                 inf->lpc_ncoef[m] = have ? sh.qncoef[m] : 0;
-                for (int j = 0; j < FLACB_MAX_LPC; j++) inf->lpc_q[m][j] = (have && j < sh.qncoef[m]) ? sh.qc[m][j] : 0;
+                for (int j = 0; j < FLACB_MAX_LPC; j++) inf->lpc_q[m][j] = (have && j < sh.qncoef[m]) ? b.qc[m * b.ldL + j] : 0;
             }
             for (int l = 0; l <= FLACB_MAX_LPC; l++) inf->autoc[l] = (L > 0 && l <= L) ? sh.autoc[l] : 0.0;
         }
@@ -1254,8 +1287,10 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
     __syncthreads();
 }
 
-template <int LMAX>
-__global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams p)
+/* TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
+ * <288, 3> (72 registers) where three frames fit an SM. */
+template <int LMAX, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
@@ -1286,7 +1321,7 @@ __global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams 
     b.flat_lo = tail_frame ? p.flat_tail_lo : p.flat_full_lo;
     b.flat_hi = tail_frame ? p.flat_tail_hi : p.flat_full_hi;
 
-    const SmemLayout lay = make_layout(p.block_size, p.channels, p.rmax, p.smem_limit);
+    const SmemLayout lay = make_layout(p.block_size, p.channels, p.bps, p.rmax, p.L, b.B, p.all_planes);
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
     b.res = (uint32_t *)(smem + lay.res);
@@ -1296,6 +1331,10 @@ __global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams 
     b.fb = (uint32_t *)(smem + lay.fb);
     b.pst = (uint32_t *)(smem + lay.pst);
     b.red = (u64 *)(smem + lay.red);
+    b.ldc = (double *)(smem + lay.ldc);
+    b.qc = (int32_t *)(smem + lay.qc);
+    b.ldL = p.L;
+    b.stg_words = lay.stg_words;
 
     /* ---- phase 0 + 1 ---- */
     if (lay.xs_all) load_planes(b, -1);
@@ -1364,7 +1403,7 @@ __global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams 
                       sh.status != FLACB_E_INTERNAL;
         if (!sh.writable && sh.status == 0) sh.status = FLACB_E_NOSPACE;
     }
-    for (int idx = b.tid; idx < STG_WORDS + 4; idx += b.B) b.stg[idx] = 0;
+    for (int idx = b.tid; idx < (int)b.stg_words + 4; idx += b.B) b.stg[idx] = 0;
     __syncthreads();
 
     /* ---- phase 3: serialise ---- */
@@ -1392,7 +1431,7 @@ __global__ void __launch_bounds__(MAXB, 1) encode_frames_kernel(const EncParams 
             }
         }
         /* make sure the serial part fits the window: header byte, warm-up, LPC parameters */
-        if (((sh.pos + 2048u) >> 5) >= sh.wbase + STG_WORDS) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
+        if (((sh.pos + 2048u) >> 5) >= sh.wbase + b.stg_words) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
         else __syncthreads();
         if (b.tid == 0) {
             const uint32_t mask = p.bps >= 32 ? 0xFFFFFFFFu : ((1u << p.bps) - 1u);

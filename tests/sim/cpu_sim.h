@@ -203,6 +203,13 @@ template <class T> static inline T __reduce_add_sync(unsigned, T v)
     sim::syncwarp();
     return r;
 }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __clzll(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -37,7 +37,6 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         if (frame_offsets) frame_offsets[0] = 0;
         return FLACB_OK;
     }
-    if (smem_limit == 0) smem_limit = 227 * 1024 - 20 * 1024;
 
     crc16_table(c_crc16_tab);
     crc16_xpow_tables(c_xpow_lo, c_xpow_hi, XPOW_HI);
@@ -65,11 +64,18 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     p.win_tail = wt.data();
     window_flat_range(wf, block_size, p.flat_full_lo, p.flat_full_hi);
     window_flat_range(wt, p.tail_size, p.flat_tail_lo, p.flat_tail_hi);
-    p.smem_limit = smem_limit;
 
-    const SmemLayout lay = make_layout(block_size, channels, rice_max, smem_limit);
-    if (lay.total > smem_limit) return FLACB_E_UNSUPPORTED;
-    const int B = threads_override ? threads_override : pick_threads(block_size, E, MAXB);
+    /* smem_limit here: 0 = the library's own choice of shape; 1 = force the single-plane mode */
+    auto layout_total = [&](int threads, int all_planes) {
+        return (size_t)make_layout(block_size, channels, bits, rice_max, max_lpc_order, threads, all_planes).total;
+    };
+    LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total);
+    if (shape.threads == 0) return FLACB_E_UNSUPPORTED;
+    if (smem_limit == 1) shape.all_planes = 0;
+    if (smem_limit == 2) shape.all_planes = 1;
+    const int B = threads_override ? threads_override : shape.threads;
+    const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, shape.all_planes);
+    p.all_planes = shape.all_planes;
 
     std::vector<uint32_t> frame_bytes(n_frames);
     std::vector<u64> frame_off(n_frames + 1, 0);
@@ -97,9 +103,9 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     }
     for (uint64_t f = 0; f < n_frames; f++) {
         if (max_lpc_order <= 12)
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<12>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<12, 576, 1>(p); });
         else
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<32>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<32, 576, 1>(p); });
     }
     if (flags & FLACB_SLOT_COMPACT) {
         sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(frame_bytes.data(), frame_off.data(), (uint32_t)n_frames); });
@@ -173,8 +179,9 @@ static int sim_decode_impl(const uint8_t *frames, uint64_t len, int streaminfo_b
         sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data(), check_crc8); });
     sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
     std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
-    for (unsigned b = 0; b < nb; b++)
-        sim::run_block(b, nb, 128, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8); });
+    const unsigned nbd = (unsigned)((n_cand + DECODE_WARPS - 1) / DECODE_WARPS);
+    for (unsigned b = 0; b < nbd; b++)
+        sim::run_block(b, nbd, 32 * DECODE_WARPS, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8); });
     DecodeResult res;
     sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
     if (res.status == STATUS_CRC8_MISMATCH || res.status == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH;

@@ -31,9 +31,11 @@ def test_sim_slot_mode_and_single_plane_mode(name):
     ref = case_stream(case)[42:]
     rc, data, _, _, _ = simlib.encode_frames(x, case["bits"], flags=simlib.FLAG_SLOT_COMPACT, **case_kwargs(case))
     assert rc == 0 and data == ref
-    # a shared memory budget that only fits one channel plane: planes are reloaded per channel
-    rc, data, _, _, st = simlib.encode_frames(x, case["bits"], smem_limit=72 * 1024, **case_kwargs(case))
-    assert rc == 0 and data == ref
+    # one channel plane in shared memory, reloaded per channel and phase (smem_limit=1), and
+    # every plane resident (smem_limit=2)
+    for mode in (1, 2):
+        rc, data, _, _, st = simlib.encode_frames(x, case["bits"], smem_limit=mode, **case_kwargs(case))
+        assert rc == 0 and data == ref, mode
 
 
 def test_sim_other_thread_counts_and_int32_input():

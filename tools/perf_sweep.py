@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--threads", default="0")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--decode", action="store_true")
+    ap.add_argument("--slots", action="store_true", help="slot + compaction placement instead of look-back")
     args = ap.parse_args()
     raw, m = bench.synth(args.workload, 0, args.seconds)
     ctx = N.Context(0)
@@ -36,19 +37,19 @@ def main():
     ctx.h2d(d_in, pin.ptr, raw.size)
     enc_args = (n, ch, bits, bs, m["L"], m["q"], m["rmin"], m["rmax"], 0)
     out_len = 0
-    for t in [int(v) for v in args.threads.split(",")]:
-        if t:
-            os.environ["FLACB200_THREADS"] = str(t)
+    for t in args.threads.split(";"):  # "0" = library default, else "threads,all_planes,variant"
+        if t != "0":
+            os.environ["FLACB200_SHAPE"] = t
         else:
-            os.environ.pop("FLACB200_THREADS", None)
+            os.environ.pop("FLACB200_SHAPE", None)
         ks = []
         for k in range(args.steps + 2):
-            rc, out_len, st = ctx.encode_raw(d_in, *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT, d_out, cap)
+            rc, out_len, st = ctx.encode_raw(d_in, *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT | (N.SLOT_COMPACT if args.slots else 0), d_out, cap)
             N.raise_for_status(rc)
             if k >= 2:
                 ks.append(st.kernel_ms)
         ms = float(np.median(ks))
-        print(json.dumps({"workload": args.workload, "threads": st.threads_per_frame, "smem": st.smem_bytes,
+        print(json.dumps({"workload": args.workload, "shape": t, "threads": st.threads_per_frame, "smem": st.smem_bytes,
                           "kernel_ms": round(ms, 4), "Msamples/s": round(n * ch / ms / 1e3, 1),
                           "GB/s": round((raw.size + out_len) / ms / 1e6, 2), "bytes_out": out_len,
                           "ood": int(st.out_of_domain)}), flush=True)
