@@ -67,12 +67,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.lines, self.first = device, None, [], 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -81,6 +81,9 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        self.first = len(self.lines)
 
     def stop(self) -> dict:
         if not self.proc:
@@ -91,7 +94,8 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        lines = self.lines[self.first:] if len(self.lines) - self.first >= 2 else self.lines[-3:]
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -140,8 +144,8 @@ def cpu_arm(name: str, rank: int, target_s: float = 15.0, threads: int | None = 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--copies", type=int, default=3, help="distinct device copies rotated between steps")
@@ -224,12 +228,14 @@ def main():
         return out_len, st
 
     # ---- resident (kernel) measurement ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to come up: start it before the warm-up
     for k in range(args.warmup):
         out_len, st = step_resident(k)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark()   # samples from here on fall into the timed region
     launches0 = N.lib().flacb_kernel_launches()
     kernel_ms = []
     ctx.timer_begin()

@@ -78,14 +78,25 @@ struct HostBuf {
     }
 };
 
+#define FLACB_SLOTS 3
+
+/* one encode chunk in flight: its stream, events and buffers */
+struct EncSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info;
+    HostBuf h_meta;
+    bool d2h_pending = false;
+};
+
 struct flacb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr; /* stream == slot[0].stream */
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     int smem_optin = 0, sm_count = 0;
     size_t static_smem12 = 0, static_smem32 = 0;
-    DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info, win_full, win_tail;
-    HostBuf h_meta;
+    EncSlot slot[FLACB_SLOTS];
+    DevBuf win_full, win_tail;
     int win_full_n = -1, win_tail_n = -1;
     bool win_full_ok = true, win_tail_ok = true;
     int flat_full[2] = {0, 0}, flat_tail[2] = {0, 0};
@@ -138,6 +149,13 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_t0, &c->ev_t1, &c->ev_c0, &c->ev_c1};
     for (cudaEvent_t *e : evs) CUDA_TRY(cudaEventCreate(e));
+    for (int i = 0; i < FLACB_SLOTS; i++) {
+        EncSlot &sl = c->slot[i];
+        if (i == 0) sl.stream = c->stream;
+        else CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        cudaEvent_t *se[] = {&sl.ev_k0, &sl.ev_k1, &sl.ev_c0, &sl.ev_c1, &sl.ev_d0, &sl.ev_d1};
+        for (cudaEvent_t *e : se) CUDA_TRY(cudaEventCreate(e));
+    }
     CUDA_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     cudaFuncAttributes fa;
@@ -163,11 +181,18 @@ extern "C" void flacb_destroy(flacb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->pcm, &c->out, &c->slots, &c->frame_bytes, &c->frame_off, &c->status, &c->lb, &c->misc,
-                      &c->info, &c->win_full, &c->win_tail, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames,
-                      &c->d_dmisc};
+    DevBuf *bufs[] = {&c->win_full, &c->win_tail, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames, &c->d_dmisc};
     for (DevBuf *b : bufs) b->release();
-    c->h_meta.release();
+    for (int i = 0; i < FLACB_SLOTS; i++) {
+        EncSlot &sl = c->slot[i];
+        DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.frame_off, &sl.status, &sl.lb, &sl.misc, &sl.info};
+        for (DevBuf *b : sb) b->release();
+        sl.h_meta.release();
+        cudaEvent_t se[] = {sl.ev_k0, sl.ev_k1, sl.ev_c0, sl.ev_c1, sl.ev_d0, sl.ev_d1};
+        for (cudaEvent_t e : se)
+            if (e) cudaEventDestroy(e);
+        if (i > 0 && sl.stream) cudaStreamDestroy(sl.stream);
+    }
     c->h_dmeta.release();
     cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_t0, c->ev_t1, c->ev_c0, c->ev_c1};
     for (cudaEvent_t e : evs)
@@ -236,7 +261,7 @@ extern "C" int flacb_sync(flacb_ctx *c)
 {
     if (!c) return FLACB_E_ASSERT;
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < FLACB_SLOTS; i++) CUDA_TRY(cudaStreamSynchronize(c->slot[i].stream));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     return FLACB_OK;
 }
@@ -257,9 +282,9 @@ static int upload_window(flacb_ctx *c, int n, DevBuf &buf, int &cached_n, bool &
     return FLACB_OK;
 }
 
-/* One launch over frames [0, n_frames) of device-resident PCM into device-resident output.
- * On return the kernels are enqueued on c->stream and the meta data copy (frame offsets,
- * statuses, counters) to pinned host memory is enqueued behind them. */
+/* One launch over frames [0, n_frames) of device-resident PCM into device-resident output, on
+ * one slot (stream + buffers).  On return the kernels are enqueued on the slot's stream and the
+ * copy of the meta data (frame offsets, statuses, counters) to pinned host memory behind them. */
 struct ChunkMeta {
     u64 *h_frame_off;  /* n_frames + 1 */
     int32_t *h_status; /* n_frames */
@@ -267,38 +292,49 @@ struct ChunkMeta {
     int threads, smem;
 };
 
-static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a, uint8_t *d_out, u64 out_cap,
-                         flacb_subframe_info *d_info, ChunkMeta &meta)
+struct EncPlan {
+    LaunchShape shape;
+    bool lmax12;
+    size_t static_smem;
+};
+
+static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
 {
-    const u64 n_frames = (a.n_sample_frames + (u64)a.block_size - 1) / (u64)a.block_size;
-    const int tail = (int)(a.n_sample_frames - (n_frames - 1) * (u64)a.block_size);
-    const bool lmax12 = a.max_lpc_order <= 12;
-    const size_t static_smem = lmax12 ? c->static_smem12 : c->static_smem32;
-    if ((size_t)c->smem_optin <= static_smem + 1024) return FLACB_E_UNSUPPORTED;
+    plan.lmax12 = a.max_lpc_order <= 12;
+    plan.static_smem = plan.lmax12 ? c->static_smem12 : c->static_smem32;
+    if ((size_t)c->smem_optin <= plan.static_smem + 1024) return FLACB_E_UNSUPPORTED;
     if (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) >= (u64)XPOW_HI * 256) return FLACB_E_UNSUPPORTED;
     auto layout_total = [&](int threads, int all_planes) {
         return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
     };
-    LaunchShape shape = pick_shape(a.block_size, E, static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total);
-    if (shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
+    plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total);
+    if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
     if (const char *e = getenv("FLACB200_SHAPE")) { /* tuning knob: "threads,all_planes,variant" */
         int t = 0, ap = 1, v = 0;
         if (sscanf(e, "%d,%d,%d", &t, &ap, &v) == 3 && t >= 32 && t % 32 == 0 && t <= (v ? 288 : 576) &&
-            layout_total(t, ap) + static_smem <= (size_t)c->smem_optin)
-            shape.threads = t, shape.all_planes = ap, shape.variant = v;
+            layout_total(t, ap) + plan.static_smem <= (size_t)c->smem_optin)
+            plan.shape.threads = t, plan.shape.all_planes = ap, plan.shape.variant = v;
     }
+    return FLACB_OK;
+}
+
+static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const uint8_t *d_pcm, const EncodeArgs &a,
+                         int full_tail, uint8_t *d_out, u64 out_cap, flacb_subframe_info *d_info, ChunkMeta &meta)
+{
+    /* full_tail: the stream's last frame is not in this chunk, every frame here is a full block */
+    const u64 n_frames = (a.n_sample_frames + (u64)a.block_size - 1) / (u64)a.block_size;
+    const int tail = full_tail ? a.block_size : (int)(a.n_sample_frames - (n_frames - 1) * (u64)a.block_size);
+    const LaunchShape &shape = plan.shape;
     const int B = shape.threads;
     const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, shape.all_planes);
 
-    int rc;
-    if ((rc = upload_window(c, a.block_size, c->win_full, c->win_full_n, c->win_full_ok, c->flat_full[0], c->flat_full[1]))) return rc;
-    if ((rc = upload_window(c, tail, c->win_tail, c->win_tail_n, c->win_tail_ok, c->flat_tail[0], c->flat_tail[1]))) return rc;
-    if ((rc = c->frame_bytes.ensure(n_frames * 4))) return rc;
-    if ((rc = c->frame_off.ensure((n_frames + 1) * 8))) return rc;
-    if ((rc = c->status.ensure(n_frames * 4))) return rc;
-    if ((rc = c->lb.ensure(n_frames * 8))) return rc;
-    if ((rc = c->misc.ensure(128))) return rc;
-    if ((rc = c->h_meta.ensure((n_frames + 1) * 8 + n_frames * 4 + 64 + 16))) return rc;
+    int rc; /* the window tables were uploaded by the caller before the first chunk */
+    if ((rc = sl.frame_bytes.ensure(n_frames * 4))) return rc;
+    if ((rc = sl.frame_off.ensure((n_frames + 1) * 8))) return rc;
+    if ((rc = sl.status.ensure(n_frames * 4))) return rc;
+    if ((rc = sl.lb.ensure(n_frames * 8))) return rc;
+    if ((rc = sl.misc.ensure(128))) return rc;
+    if ((rc = sl.h_meta.ensure((n_frames + 1) * 8 + n_frames * 4 + 64 + 16))) return rc;
 
     EncParams p;
     memset(&p, 0, sizeof(p));
@@ -316,24 +352,26 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
     p.flags = a.flags;
     p.n_frames = (uint32_t)n_frames;
     p.tail_size = tail;
+    const bool own_tail = tail != a.block_size; /* only the stream's last frame can be short */
     p.win_full = (const double *)c->win_full.p;
-    p.win_tail = (const double *)c->win_tail.p;
+    p.win_tail = own_tail ? (const double *)c->win_tail.p : p.win_full;
     p.win_full_bad = !c->win_full_ok;
-    p.win_tail_bad = !c->win_tail_ok;
+    p.win_tail_bad = own_tail ? !c->win_tail_ok : p.win_full_bad;
     p.flat_full_lo = c->flat_full[0], p.flat_full_hi = c->flat_full[1];
-    p.flat_tail_lo = c->flat_tail[0], p.flat_tail_hi = c->flat_tail[1];
-    p.frame_bytes = (uint32_t *)c->frame_bytes.p;
-    p.frame_off = (u64 *)c->frame_off.p;
-    p.frame_status = (int32_t *)c->status.p;
-    p.lb_state = (u64 *)c->lb.p;
-    p.ticket = (uint32_t *)c->misc.p;
-    p.stats = (u64 *)((uint8_t *)c->misc.p + 64);
+    p.flat_tail_lo = own_tail ? c->flat_tail[0] : p.flat_full_lo;
+    p.flat_tail_hi = own_tail ? c->flat_tail[1] : p.flat_full_hi;
+    p.frame_bytes = (uint32_t *)sl.frame_bytes.p;
+    p.frame_off = (u64 *)sl.frame_off.p;
+    p.frame_status = (int32_t *)sl.status.p;
+    p.lb_state = (u64 *)sl.lb.p;
+    p.ticket = (uint32_t *)sl.misc.p;
+    p.stats = (u64 *)((uint8_t *)sl.misc.p + 64);
     p.info = d_info;
     p.all_planes = shape.all_planes;
     if (a.flags & FLACB_SLOT_COMPACT) {
         p.slot_stride = (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) + 15) & ~15ull;
-        if ((rc = c->slots.ensure(p.slot_stride * n_frames))) return rc;
-        p.out = (uint8_t *)c->slots.p;
+        if ((rc = sl.slots.ensure(p.slot_stride * n_frames))) return rc;
+        p.out = (uint8_t *)sl.slots.p;
         p.out_cap = p.slot_stride * n_frames;
     } else {
         p.slot_stride = 0;
@@ -341,41 +379,58 @@ static int launch_encode(flacb_ctx *c, const uint8_t *d_pcm, const EncodeArgs &a
         p.out_cap = out_cap;
     }
 
-    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, 128, c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->lb.p, 0, n_frames * 8, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev_k0, c->stream));
+    CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 128, sl.stream));
+    CUDA_TRY(cudaMemsetAsync(sl.lb.p, 0, n_frames * 8, sl.stream));
+    CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
 #define FLACB_LAUNCH(LM, TB, MB)                                                                                   \
     do {                                                                                                           \
         CUDA_TRY(cudaFuncSetAttribute(encode_frames_kernel<LM, TB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       (int)lay.total));                                                            \
-        encode_frames_kernel<LM, TB, MB><<<(unsigned)n_frames, B, lay.total, c->stream>>>(p);                     \
+        encode_frames_kernel<LM, TB, MB><<<(unsigned)n_frames, B, lay.total, sl.stream>>>(p);                     \
     } while (0)
-    if (lmax12 && shape.variant) FLACB_LAUNCH(12, 288, 3);
-    else if (lmax12) FLACB_LAUNCH(12, 576, 1);
+    if (plan.lmax12 && shape.variant) FLACB_LAUNCH(12, 288, 3);
+    else if (plan.lmax12) FLACB_LAUNCH(12, 576, 1);
     else if (shape.variant) FLACB_LAUNCH(32, 288, 3);
     else FLACB_LAUNCH(32, 576, 1);
 #undef FLACB_LAUNCH
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (a.flags & FLACB_SLOT_COMPACT) {
-        scan_frame_bytes_kernel<<<1, 256, 0, c->stream>>>(p.frame_bytes, p.frame_off, p.n_frames);
+        scan_frame_bytes_kernel<<<1, 256, 0, sl.stream>>>(p.frame_bytes, p.frame_off, p.n_frames);
         CUDA_TRY(cudaGetLastError());
-        compact_slots_kernel<<<(unsigned)n_frames, 256, 0, c->stream>>>((const uint8_t *)c->slots.p, p.slot_stride, p.frame_bytes,
-                                                                         p.frame_off, d_out, out_cap, p.frame_status);
+        compact_slots_kernel<<<(unsigned)n_frames, 256, 0, sl.stream>>>((const uint8_t *)sl.slots.p, p.slot_stride, p.frame_bytes,
+                                                                        p.frame_off, d_out, out_cap, p.frame_status);
         CUDA_TRY(cudaGetLastError());
         g_launches += 2;
     }
-    CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
+    CUDA_TRY(cudaEventRecord(sl.ev_k1, sl.stream));
 
-    uint8_t *h = (uint8_t *)c->h_meta.p;
+    uint8_t *h = (uint8_t *)sl.h_meta.p;
     meta.h_frame_off = (u64 *)h;
     meta.h_stats = (u64 *)(h + (n_frames + 1) * 8);
     meta.h_status = (int32_t *)(h + (n_frames + 1) * 8 + 64);
     meta.threads = B;
     meta.smem = (int)lay.total;
-    CUDA_TRY(cudaMemcpyAsync(meta.h_frame_off, c->frame_off.p, (n_frames + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 64, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(meta.h_status, c->status.p, n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(meta.h_frame_off, sl.frame_off.p, (n_frames + 1) * 8, cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 64, cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(meta.h_status, sl.status.p, n_frames * 4, cudaMemcpyDeviceToHost, sl.stream));
+    return FLACB_OK;
+}
+
+/* first frame of the chunk, in stream order, on which the reference raises (strict mode) */
+static int first_bad(const ChunkMeta &meta, u64 n_frames, uint32_t flags, int64_t &bad, u64 &valid)
+{
+    valid = meta.h_frame_off[n_frames];
+    bad = -1;
+    for (u64 f = 0; f < n_frames; f++) {
+        const int s = meta.h_status[f];
+        const bool ood = s >= FLACB_E_ASSERT && s <= FLACB_E_ZERODIV;
+        if (s != 0 && !(ood && (flags & FLACB_LENIENT))) {
+            bad = (int64_t)f;
+            valid = meta.h_frame_off[f];
+            return s;
+        }
+    }
     return FLACB_OK;
 }
 
@@ -403,84 +458,170 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     if ((!pcm) || (!out && out_cap)) return FLACB_E_ASSERT;
     CUDA_TRY(cudaSetDevice(c->device));
     const int cbytes = (flags & FLACB_PCM_INT32) ? 4 : (bits + 7) / 8;
+    const u64 frame_pcm = (u64)block_size * (u64)channels * (u64)cbytes;
     const u64 pcm_bytes = n_sample_frames * (u64)channels * (u64)cbytes;
-    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f;
+    EncPlan plan;
+    if ((rc = plan_encode(c, a, plan))) return rc;
+    {   /* Tukey windows of the full block and of the stream's last, shorter block */
+        const int real_tail = (int)(n_sample_frames - (n_frames - 1) * (u64)block_size);
+        if ((rc = upload_window(c, block_size, c->win_full, c->win_full_n, c->win_full_ok, c->flat_full[0], c->flat_full[1]))) return rc;
+        if (real_tail != block_size &&
+            (rc = upload_window(c, real_tail, c->win_tail, c->win_tail_n, c->win_tail_ok, c->flat_tail[0], c->flat_tail[1])))
+            return rc;
+    }
+    const bool host_in = !(flags & FLACB_INPUT_ON_DEVICE), host_out = !(flags & FLACB_OUTPUT_ON_DEVICE);
 
-    const uint8_t *d_pcm = (const uint8_t *)pcm;
-    if (!(flags & FLACB_INPUT_ON_DEVICE)) {
-        if ((rc = c->pcm.ensure(pcm_bytes))) return rc;
-        CUDA_TRY(cudaEventRecord(c->ev_c0, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev_c1, c->stream));
-        d_pcm = (const uint8_t *)c->pcm.p;
+    /* Host buffers on both sides: cut the frame range into chunks and keep three in flight, so
+     * that the H2D copy of one chunk, the kernel of another and the D2H copy of a third overlap.
+     * Chunks are whole waves of resident CTAs.  Everything else: one chunk. */
+    u64 chunk_frames = n_frames;
+    if (host_in && host_out && !info && !(flags & FLACB_SLOT_COMPACT)) {
+        const u64 wave = (u64)c->sm_count * (u64)plan.shape.ctas_per_sm;
+        u64 want = (16ull << 20) / (frame_pcm ? frame_pcm : 1);
+        if (const char *e = getenv("FLACB200_CHUNK_FRAMES")) want = (u64)atoll(e);
+        want = (want + wave - 1) / wave * wave;
+        if (want < wave) want = wave;
+        if (want * 2 <= n_frames) chunk_frames = want;
     }
-    uint8_t *d_out = out;
-    u64 d_cap = out_cap;
-    if (!(flags & FLACB_OUTPUT_ON_DEVICE)) {
-        d_cap = flacb_encode_bound(n_sample_frames, channels, bits, block_size, rice_max);
-        if ((rc = c->out.ensure(d_cap))) return rc;
-        d_out = (uint8_t *)c->out.p;
-    }
+    const u64 n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f;
+    u64 host_off = 0; /* bytes produced so far */
+    int64_t bad_frame = -1;
+    u64 ood = 0, hist[6] = {0, 0, 0, 0, 0, 0};
+    int threads = 0, smem = 0;
+    int status = FLACB_OK;
+
+    struct Pending {
+        ChunkMeta meta;
+        u64 f0, nfr;
+        bool active;
+    } pend[FLACB_SLOTS];
+    for (int i = 0; i < FLACB_SLOTS; i++) pend[i].active = false;
+
+    /* retire chunk in slot s: wait for its kernel, read sizes and statuses, start its D2H */
+    auto retire = [&](int s) -> int {
+        EncSlot &sl = c->slot[s];
+        Pending &pd = pend[s];
+        if (!pd.active) return FLACB_OK;
+        pd.active = false;
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1));
+        k_ms += ms;
+        if (host_in) {
+            CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_c0, sl.ev_c1));
+            h2d_ms += ms;
+        }
+        if (status != FLACB_OK) return FLACB_OK; /* an earlier chunk already failed: discard */
+        int64_t bad;
+        u64 valid;
+        const int st = first_bad(pd.meta, pd.nfr, flags, bad, valid);
+        if (frame_offsets)
+            for (u64 f = 0; f <= pd.nfr; f++) frame_offsets[pd.f0 + f] = host_off + pd.meta.h_frame_off[f];
+        for (int o = 0; o < 6; o++) hist[o] += pd.meta.h_stats[o];
+        ood += pd.meta.h_stats[6];
+        threads = pd.meta.threads, smem = pd.meta.smem;
+        if (host_out) {
+            if (host_off + valid > out_cap) {
+                status = st != FLACB_OK ? st : FLACB_E_NOSPACE;
+                bad_frame = (int64_t)pd.f0 + (bad >= 0 ? bad : 0);
+                return FLACB_OK;
+            }
+            if (valid) {
+                CUDA_TRY(cudaEventRecord(sl.ev_d0, sl.stream));
+                CUDA_TRY(cudaMemcpyAsync(out + host_off, sl.out.p, valid, cudaMemcpyDeviceToHost, sl.stream));
+                CUDA_TRY(cudaEventRecord(sl.ev_d1, sl.stream));
+                sl.d2h_pending = true;
+            }
+        }
+        host_off += valid;
+        if (st != FLACB_OK) {
+            status = st;
+            bad_frame = (int64_t)pd.f0 + bad;
+        }
+        return FLACB_OK;
+    };
+    auto finish_d2h = [&](int s) -> int {
+        EncSlot &sl = c->slot[s];
+        if (!sl.d2h_pending) return FLACB_OK;
+        sl.d2h_pending = false;
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_d0, sl.ev_d1));
+        d2h_ms += ms;
+        return FLACB_OK;
+    };
+
     flacb_subframe_info *d_info = nullptr;
     if (info) {
-        if ((rc = c->info.ensure(n_frames * (u64)channels * sizeof(flacb_subframe_info)))) return rc;
-        d_info = (flacb_subframe_info *)c->info.p;
+        if ((rc = c->slot[0].info.ensure(n_frames * (u64)channels * sizeof(flacb_subframe_info)))) return rc;
+        d_info = (flacb_subframe_info *)c->slot[0].info.p;
     }
-    ChunkMeta meta;
-    if ((rc = launch_encode(c, d_pcm, a, d_out, d_cap, d_info, meta))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaEventElapsedTime(&k_ms, c->ev_k0, c->ev_k1));
-    if (!(flags & FLACB_INPUT_ON_DEVICE)) CUDA_TRY(cudaEventElapsedTime(&h2d_ms, c->ev_c0, c->ev_c1));
-
-    /* status of the first frame, in stream order, on which the reference raises */
-    u64 valid = meta.h_frame_off[n_frames];
-    int64_t bad = -1;
-    for (u64 f = 0; f < n_frames; f++) {
-        const int s = meta.h_status[f];
-        const bool ood = s >= FLACB_E_ASSERT && s <= FLACB_E_ZERODIV;
-        if (s != 0 && !(ood && (flags & FLACB_LENIENT))) {
-            rc = s;
-            bad = (int64_t)f;
-            valid = meta.h_frame_off[f];
-            break;
+    for (u64 ci = 0; ci < n_chunks; ci++) {
+        const int s = (int)(ci % FLACB_SLOTS);
+        EncSlot &sl = c->slot[s];
+        /* the slot's previous chunk must be retired (and its output copied) before reuse;
+         * chunks are retired in order */
+        if ((rc = retire(s))) return rc;
+        if ((rc = finish_d2h(s))) return rc;
+        if (status != FLACB_OK) break;
+        const u64 f0 = ci * chunk_frames;
+        const u64 nfr = f0 + chunk_frames <= n_frames ? chunk_frames : n_frames - f0;
+        const u64 s0 = f0 * (u64)block_size;
+        const u64 ns = (f0 + nfr == n_frames) ? n_sample_frames - s0 : nfr * (u64)block_size;
+        EncodeArgs ca = a;
+        ca.n_sample_frames = ns;
+        ca.first_frame_number = first_frame_number + f0;
+        const uint8_t *d_pcm = (const uint8_t *)pcm + s0 * (u64)channels * (u64)cbytes;
+        if (host_in) {
+            const u64 nb = ns * (u64)channels * (u64)cbytes;
+            if ((rc = sl.pcm.ensure(nb))) return rc;
+            CUDA_TRY(cudaEventRecord(sl.ev_c0, sl.stream));
+            CUDA_TRY(cudaMemcpyAsync(sl.pcm.p, d_pcm, nb, cudaMemcpyHostToDevice, sl.stream));
+            CUDA_TRY(cudaEventRecord(sl.ev_c1, sl.stream));
+            d_pcm = (const uint8_t *)sl.pcm.p;
         }
+        uint8_t *d_out = out;
+        u64 d_cap = out_cap;
+        if (host_out) {
+            d_cap = flacb_encode_bound(ns, channels, bits, block_size, rice_max);
+            if ((rc = sl.out.ensure(d_cap))) return rc;
+            d_out = (uint8_t *)sl.out.p;
+        }
+        if ((rc = launch_encode(c, sl, plan, d_pcm, ca, f0 + nfr != n_frames, d_out, d_cap, d_info, pend[s].meta))) return rc;
+        pend[s].f0 = f0;
+        pend[s].nfr = nfr;
+        pend[s].active = true;
     }
-    if (!(flags & FLACB_OUTPUT_ON_DEVICE)) {
-        if (valid > out_cap) {
-            if (rc == FLACB_OK) rc = FLACB_E_NOSPACE;
-            valid = 0;
-        }
-        if (valid) {
-            CUDA_TRY(cudaEventRecord(c->ev_c0, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(out, d_out, valid, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaEventRecord(c->ev_c1, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c->ev_c0, c->ev_c1));
-        }
+    /* drain in chunk order */
+    for (u64 k = 0; k < FLACB_SLOTS; k++) {
+        const int s = (int)((n_chunks + k) % FLACB_SLOTS);
+        if ((rc = retire(s))) return rc;
     }
-    if (info) {
+    for (int s = 0; s < FLACB_SLOTS; s++)
+        if ((rc = finish_d2h(s))) return rc;
+    if (info && status != FLACB_E_CUDA) {
         CUDA_TRY(cudaMemcpyAsync(info, d_info, n_frames * (u64)channels * sizeof(flacb_subframe_info), cudaMemcpyDeviceToHost,
-                                 c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+                                 c->slot[0].stream));
+        CUDA_TRY(cudaStreamSynchronize(c->slot[0].stream));
     }
-    if (out_len) *out_len = valid;
-    if (frame_offsets) memcpy(frame_offsets, meta.h_frame_off, (n_frames + 1) * 8);
+    if (out_len) *out_len = host_off;
     if (stats) {
         stats->frames = n_frames;
         stats->subframes = n_frames * (u64)channels;
-        for (int o = 0; o < 5; o++) stats->subframes_fixed[o] = meta.h_stats[o];
-        stats->subframes_lpc = meta.h_stats[5];
-        stats->out_of_domain = meta.h_stats[6];
+        for (int o = 0; o < 5; o++) stats->subframes_fixed[o] = hist[o];
+        stats->subframes_lpc = hist[5];
+        stats->out_of_domain = ood;
         stats->bytes_in = pcm_bytes;
-        stats->bytes_out = valid;
-        stats->first_bad_frame = bad;
+        stats->bytes_out = host_off;
+        stats->first_bad_frame = bad_frame;
         stats->kernel_ms = k_ms;
         stats->h2d_ms = h2d_ms;
         stats->d2h_ms = d2h_ms;
-        stats->threads_per_frame = meta.threads;
-        stats->smem_bytes = meta.smem;
+        stats->threads_per_frame = threads;
+        stats->smem_bytes = smem;
     }
-    return rc;
+    return status;
 }
 
 /* ------------------------------------------------------------------------------------- */

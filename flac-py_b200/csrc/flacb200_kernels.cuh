@@ -517,19 +517,27 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
             for (int l = 0; l < LG; l++) redd[b.warp * LG + l] = make_double2(s[l], c[l]);
         }
         __syncthreads();
-        if (b.tid < LG && lag0 + b.tid <= L) {
+        for (int l = b.warp; l < LG && lag0 + l <= L; l += b.nwarps) { /* a warp per lag combines the warps' sums */
             double S = 0.0, C = 0.0;
-            for (int w = 0; w < b.nwarps; w++) {
-                const double2 v = redd[w * LG + b.tid];
-                dd_add(S, C, v.x);
-                C = __dadd_rn(C, v.y);
+            if (b.lane < b.nwarps) {
+                const double2 v = redd[b.lane * LG + l];
+                S = v.x, C = v.y;
             }
-            /* the exact integer part, split into two doubles that each hold it exactly */
-            const i64 iv = b.sh.isum[lag0 + b.tid];
-            const i64 hi = iv & ~(i64)0x7FF, lo = iv & (i64)0x7FF;
-            dd_add(S, C, (double)hi);
-            dd_add(S, C, (double)lo);
-            b.sh.autoc[lag0 + b.tid] = __dadd_rn(S, C);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double s2 = __shfl_xor_sync(FULL, S, off);
+                const double c2 = __shfl_xor_sync(FULL, C, off);
+                dd_add(S, C, s2);
+                C = __dadd_rn(C, c2);
+            }
+            if (b.lane == 0) {
+                /* the exact integer part, split into two doubles that each hold it exactly */
+                const i64 iv = b.sh.isum[lag0 + l];
+                const i64 hi = iv & ~(i64)0x7FF, lo = iv & (i64)0x7FF;
+                dd_add(S, C, (double)hi);
+                dd_add(S, C, (double)lo);
+                b.sh.autoc[lag0 + l] = __dadd_rn(S, C);
+            }
         }
         __syncthreads();
     }
@@ -539,38 +547,41 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
 /* encoder.py:453-479 levinson_durbin, run once to the maximum order: the coefficient vector
  * after iteration k equals levinson_durbin(autoc[:k+2]) bit for bit.  Strict IEEE operation
  * order; `lambda ** 2` is evaluated as lambda*lambda (glibc pow differs by 1 ulp on ~0.08% of
- * arguments; documented in DESIGN.md).  One thread.                                          */
+ * arguments; documented in DESIGN.md).  One warp.                                            */
 
 __device__ void levinson(Blk &b, int L)
 {
+    /* warp 0: lane j keeps coefs[j] (j < 32; coefs[32] only appears in the last iteration of
+     * L = 32 and is handled on the side).  The products of the lambda sum are formed in parallel,
+     * the sum itself runs in the reference's order (every partial sum is rounded), the symmetric
+     * pair update is one step per lane. */
     Shared &sh = b.sh;
-    double coefs[FLACB_MAX_LPC + 1];
-#pragma unroll 1
-    for (int i = 0; i <= L; i++) coefs[i] = 0.0;
-    coefs[0] = 1.0;
+    const int lane = b.lane;
+    double cj = lane == 0 ? 1.0 : 0.0; /* coefs[lane] */
     double error = sh.autoc[0];
     int stat = 0;
 #pragma unroll 1
     for (int k = 0; k < L; k++) {
+        const double prod = (lane <= k) ? __dmul_rn(cj, sh.autoc[k + 1 - lane]) : 0.0;
         double lambda = 0.0;
 #pragma unroll 1
-        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, __dmul_rn(coefs[j], sh.autoc[k + 1 - j]));
-        if (error == 0.0) { stat = FLACB_E_ZERODIV; break; }
+        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, __shfl_sync(FULL, prod, j)); /* encoder.py:467 */
+        if (error == 0.0) { stat = FLACB_E_ZERODIV; break; }                                /* encoder.py:469 */
         lambda = __ddiv_rn(lambda, error);
-#pragma unroll 1
-        for (int m = 0; m <= (k + 1) / 2; m++) {
-            const double lo = coefs[m], hi = coefs[k + 1 - m];
-            const double temp = __dadd_rn(hi, __dmul_rn(lambda, lo));
-            coefs[m] = __dadd_rn(lo, __dmul_rn(lambda, hi));
-            coefs[k + 1 - m] = temp;
-        }
+        /* encoder.py:471-474: coefs[i] <- coefs[i] + lambda * coefs[k+1-i] for i in 0..k+1 */
+        const int partner = k + 1 - lane;
+        double cp = __shfl_sync(FULL, cj, partner & 31);
+        if (partner < 0 || partner > 31) cp = 0.0; /* coefs[32] is still zero when it is read */
+        const double c0 = __shfl_sync(FULL, cj, 0);
+        if (lane <= k + 1) cj = __dadd_rn(cj, __dmul_rn(lambda, cp));
+        const double c32 = __dadd_rn(0.0, __dmul_rn(lambda, c0)); /* new coefs[32] when k + 1 == 32 */
         const double l2 = __dmul_rn(lambda, lambda);
         if (isinf(l2) && !isinf(lambda)) { stat = FLACB_E_OVERFLOW; break; }
-        error = __dmul_rn(error, __dsub_rn(1.0, l2));
-#pragma unroll 1
-        for (int j = 0; j <= k; j++) b.ldc[k * b.ldL + j] = coefs[j + 1];
+        error = __dmul_rn(error, __dsub_rn(1.0, l2));                                       /* encoder.py:476 */
+        if (lane >= 1 && lane <= k + 1) b.ldc[k * b.ldL + lane - 1] = cj;
+        if (k + 1 == 32 && lane == 0) b.ldc[k * b.ldL + 31] = c32;
     }
-    sh.lev_stat = stat;
+    if (lane == 0) sh.lev_stat = stat;
 }
 
 /* encoder.py:482-534 quantize_lpc_coefficients for order m (one thread per order) */
@@ -1195,7 +1206,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
             if (b.tid == 0) set_status(b, FLACB_E_ZERODIV); /* encoder.py:437 */
         } else {
             autocorrelation<4, (LMAX <= 12 ? 13 : 11)>(b, x, L);
-            if (b.tid == 0) levinson(b, L);
+            if (b.warp == 0) levinson(b, L);
             __syncthreads();
             if (sh.lev_stat == 0) {
                 if (b.tid < L) quantize_order(b, b.tid + 1, p.P);
