@@ -131,14 +131,17 @@ def cpu_arm(name: str, rank: int, target_s: float = 15.0, threads: int | None = 
     per_round = max(time.perf_counter() - t0, 1e-4)
     rounds = int(max(1, min(target_s / per_round, (rate * secs) // (bs * cores))))
     x = S.pcm(bs * cores * rounds, ch, bits, rate, "mixed", seed)
-    t0 = time.perf_counter()
-    enc = O.encode_frames(x, bits, bs, L, q, rmin, rmax, threads=cores)
-    dt = time.perf_counter() - t0
-    ms = x.shape[0] * ch / dt / 1e6
+    dt, passes = 0.0, 0
+    while dt < target_s * 0.6 or passes == 0:  # repeat the slice until enough CPU time is on the clock
+        t0 = time.perf_counter()
+        enc = O.encode_frames(x, bits, bs, L, q, rmin, rmax, threads=cores)
+        dt += time.perf_counter() - t0
+        passes += 1
+    ms = x.shape[0] * ch * passes / dt / 1e6
     return {"value": ms, "unit": "Msamples/s", "cores": cores, "kind": "port",
             "sample": f"first {x.shape[0]} sample frames ({cores * rounds} frames, {x.shape[0] / rate:.1f} s of audio) of the "
-                      f"workload, oracle/flac_oracle.c with {cores} threads, {dt:.2f} s wall, {len(enc.data)} bytes out",
-            "seconds": dt, "realtime_x": x.shape[0] / rate / dt}
+                      f"workload, {passes} passes, oracle/flac_oracle.c with {cores} threads, {dt:.2f} s wall, {len(enc.data)} bytes out per pass",
+            "seconds": dt, "realtime_x": x.shape[0] * passes / rate / dt}
 
 
 def main():

@@ -368,6 +368,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     p.stats = (u64 *)((uint8_t *)sl.misc.p + 64);
     p.info = d_info;
     p.all_planes = shape.all_planes;
+    p.lay = lay;
     if (a.flags & FLACB_SLOT_COMPACT) {
         p.slot_stride = (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) + 15) & ~15ull;
         if ((rc = sl.slots.ensure(p.slot_stride * n_frames))) return rc;

@@ -308,8 +308,15 @@ struct History { /* last 32 reconstructed samples, circular */
 /* decoder.py:358-421 get_residual with the prediction of decoder.py:493-498 applied on the fly:
  * out[i] = residual + (sum_j out[i-1-j] * coef[j] >> shift) */
 __device__ int decode_residual(BitReader &g, int bs, int order, const int32_t *coef, int shift, History &hist,
-                               int32_t *out)
+                               int32_t *out, bool is_fixed)
 {
+    i64 x1 = 0, x2 = 0, x3 = 0, x4 = 0; /* out[pos-1] .. out[pos-4] for the fixed predictors */
+    if (is_fixed) {
+        if (order >= 1) x1 = hist.back(0);
+        if (order >= 2) x2 = hist.back(1);
+        if (order >= 3) x3 = hist.back(2);
+        if (order >= 4) x4 = hist.back(3);
+    }
     const uint32_t m = g.read(2);
     if (g.eof) return FLACB_E_EOF;
     if (m > 1) return FLACB_E_VALUE; /* RiceCodingMethod(x) */
@@ -341,10 +348,19 @@ __device__ int decode_residual(BitReader &g, int bs, int order, const int32_t *c
                 r = (i64)(u >> 1) ^ -(i64)(u & 1); /* utils.py:87-88 zigzag_decode */
             }
             if (g.eof) return FLACB_E_EOF;
-            i64 acc = 0;
-            for (int j = 0; j < order; j++) acc += hist.back(j) * (i64)coef[j];
-            const i64 v = r + (acc >> shift);
-            hist.push(v);
+            i64 v;
+            if (is_fixed) {
+                /* fixed predictors (common.py:15-21) on the last four samples, kept in registers */
+                const i64 pred = order == 0 ? 0 : order == 1 ? x1 : order == 2 ? 2 * x1 - x2
+                                 : order == 3 ? 3 * x1 - 3 * x2 + x3 : 4 * x1 - 6 * x2 + 4 * x3 - x4;
+                v = r + pred;
+                x4 = x3, x3 = x2, x2 = x1, x1 = v;
+            } else {
+                i64 acc = 0;
+                for (int j = 0; j < order; j++) acc += hist.back(j) * (i64)coef[j];
+                v = r + (acc >> shift);
+                hist.push(v);
+            }
             out[pos++] = (int32_t)v;
         }
     }
@@ -414,7 +430,7 @@ __device__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *o
         /* a negative shift only fails once the prediction runs (decoder.py:497); the residual is
          * parsed first */
     }
-    const int rc = decode_residual(g, bs, order, coef, shift < 0 ? 0 : shift, hist, out);
+    const int rc = decode_residual(g, bs, order, coef, shift < 0 ? 0 : shift, hist, out, type <= 12);
     if (rc) return rc;
     if (shift < 0) return FLACB_E_VALUE;
     return FLACB_OK;

@@ -69,6 +69,50 @@ constexpr u64 LB_VALUE = (1ull << 62) - 1;
  * warp on distinct banks */
 __host__ __device__ __forceinline__ uint32_t padidx(uint32_t i) { return i + (i >> 5); }
 
+struct SmemLayout {
+    uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, ldc, qc, total;
+    int xs_all;
+};
+
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+/* Shared memory plan.  all_planes: every channel plane resident; otherwise one plane that is
+ * (re)loaded per channel and phase, which leaves room for more CTAs per SM.  `threads` sizes the
+ * staging window: a tile of threads * E samples packs into at most (bps + 4) bits per sample
+ * (SURVEY.md 9.5), so a window of that size never needs a second pass. */
+__host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bps, int rmax, int L, int threads,
+                                                   int all_planes)
+{
+    SmemLayout l;
+    l.xwords = padidx((uint32_t)(GUARD + nmax + TAILPAD)) + 1;
+    const uint32_t plane = align16(l.xwords * 4);
+    int tile = threads * E < nmax ? threads * E : nmax;
+    uint32_t words = ((uint32_t)tile * (uint32_t)(bps + 4) + 31) / 32 + 96; /* + serial header part */
+    /* better still: the whole frame (one flush, at the end), up to the cap */
+    const uint32_t per = ((uint32_t)nmax * (uint32_t)(bps + 4) + 7) / 8 + (1u << rmax) + 256;
+    const uint32_t frame_words = (per * (uint32_t)channels + 64 + 3) / 4 + 96;
+    if (words < frame_words) words = frame_words;
+    if (words < 512) words = 512;
+    if (words > (uint32_t)STG_WORDS) words = (uint32_t)STG_WORDS;
+    l.stg_words = words;
+    l.xs_all = all_planes;
+    uint32_t off = 0;
+    l.xs = off; off += all_planes ? plane * (uint32_t)channels : plane;
+    l.res = off; off += align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
+    l.cum = off; off += align16(((uint32_t)nmax / E + 4) * 8);
+    l.kall = off; off += align16(2u << rmax);
+    l.stg = off; off += align16((words + 4) * 4);
+    /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
+    uint32_t red_b = align16((MAXB / 32) * RED_STRIDE * 8);
+    const uint32_t pack_b = align16(MAXB * 4) + align16((MAXB + 1) * 4);
+    if (red_b < pack_b) red_b = pack_b;
+    l.red = off; l.fb = off; l.pst = off + align16(MAXB * 4); off += red_b;
+    l.ldc = off; off += align16((uint32_t)(L * L) * 8);
+    l.qc = off; off += align16((uint32_t)(L * L) * 4);
+    l.total = off;
+    return l;
+}
+
 struct EncParams {
     const uint8_t *pcm;        /* interleaved, cbytes per sample, little endian */
     u64 n_sample_frames;
@@ -94,47 +138,8 @@ struct EncParams {
     u64 *stats;                /* device counters: [0..4] fixed order histogram, [5] lpc, [6] ood */
     flacb_subframe_info *info; /* optional, device memory */
     int all_planes;            /* every channel plane resident in shared memory */
+    SmemLayout lay;            /* make_layout(...) of this launch, computed once on the host */
 };
-
-struct SmemLayout {
-    uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, ldc, qc, total;
-    int xs_all;
-};
-
-__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
-
-/* Shared memory plan.  all_planes: every channel plane resident; otherwise one plane that is
- * (re)loaded per channel and phase, which leaves room for more CTAs per SM.  `threads` sizes the
- * staging window: a tile of threads * E samples packs into at most (bps + 4) bits per sample
- * (SURVEY.md 9.5), so a window of that size never needs a second pass. */
-__host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bps, int rmax, int L, int threads,
-                                                   int all_planes)
-{
-    SmemLayout l;
-    l.xwords = padidx((uint32_t)(GUARD + nmax + TAILPAD)) + 1;
-    const uint32_t plane = align16(l.xwords * 4);
-    int tile = threads * E < nmax ? threads * E : nmax;
-    uint32_t words = ((uint32_t)tile * (uint32_t)(bps + 4) + 31) / 32 + 96; /* + serial header part */
-    if (words < 512) words = 512;
-    if (words > (uint32_t)STG_WORDS) words = (uint32_t)STG_WORDS;
-    l.stg_words = words;
-    l.xs_all = all_planes;
-    uint32_t off = 0;
-    l.xs = off; off += all_planes ? plane * (uint32_t)channels : plane;
-    l.res = off; off += align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
-    l.cum = off; off += align16(((uint32_t)nmax / E + 4) * 8);
-    l.kall = off; off += align16(2u << rmax);
-    l.stg = off; off += align16((words + 4) * 4);
-    /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
-    uint32_t red_b = align16((MAXB / 32) * RED_STRIDE * 8);
-    const uint32_t pack_b = align16(MAXB * 4) + align16((MAXB + 1) * 4);
-    if (red_b < pack_b) red_b = pack_b;
-    l.red = off; l.fb = off; l.pst = off + align16(MAXB * 4); off += red_b;
-    l.ldc = off; off += align16((uint32_t)(L * L) * 8);
-    l.qc = off; off += align16((uint32_t)(L * L) * 4);
-    l.total = off;
-    return l;
-}
 
 #ifndef FLACB_HOST_ONLY
 
@@ -171,7 +176,7 @@ struct Shared {
     uint32_t pos, wbase, crc;
     u64 frame_off;
     uint32_t frame_bytes, payload_bytes;
-    int status, writable, range_flag;
+    int status, writable, range_flag, have_off;
     uint32_t frame;
     uint32_t scan_warp[33];
     u64 scan_warp64[33];
@@ -342,27 +347,47 @@ __device__ void load_planes(Blk &b, int c_only)
         int i = j < GUARD ? j : b.n + j; /* logical index GUARD + n + (j - GUARD) */
         b.xs[(uint32_t)pl * b.xwords + padidx((uint32_t)i)] = 0;
     }
-    if (c_only < 0) {
-        const int total = b.n * ch;
-        if (ch == 1) {
-            for (int s = b.tid; s < total; s += b.B)
-                b.xs[padidx((uint32_t)(GUARD + s))] = load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
-        } else if (ch == 2) {
-            for (int s = b.tid; s < total; s += b.B)
-                b.xs[(uint32_t)(s & 1) * b.xwords + padidx((uint32_t)(GUARD + (s >> 1)))] =
-                    load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
-        } else {
-            for (int s = b.tid; s < total; s += b.B) {
-                int i = s / ch, c = s - i * ch;
-                b.xs[(uint32_t)c * b.xwords + padidx((uint32_t)(GUARD + i))] =
-                    load_sample(base, (u64)s, p.cbytes, p.bps, aligned);
+    const int total = b.n * ch;
+    int done = 0; /* samples [0, done) are handled by a vector path, the rest one by one */
+    auto put = [&](int sidx, int32_t v) {
+        /* sample `sidx` of the interleaved frame -> its plane */
+        int i, c;
+        if (ch == 1) i = sidx, c = 0;
+        else if (ch == 2) i = sidx >> 1, c = sidx & 1;
+        else if (ch == 4) i = sidx >> 2, c = sidx & 3;
+        else if (ch == 8) i = sidx >> 3, c = sidx & 7;
+        else i = sidx / ch, c = sidx - i * ch;
+        if (c_only < 0) b.xs[(uint32_t)c * b.xwords + padidx((uint32_t)(GUARD + i))] = v;
+        else if (c == c_only) b.xs[padidx((uint32_t)(GUARD + i))] = v;
+    };
+    if (p.cbytes == 2 && (((uintptr_t)base) & 15) == 0) {
+        /* 16-bit: eight samples per 16-byte load */
+        const int groups = total >> 3;
+        const uint4 *src = (const uint4 *)base;
+        for (int g = b.tid; g < groups; g += b.B) {
+            const uint4 w = src[g];
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                put(8 * g + 2 * k, (int32_t)(int16_t)(ww[k] & 0xFFFFu));
+                put(8 * g + 2 * k + 1, (int32_t)ww[k] >> 16);
             }
         }
-    } else {
-        for (int i = b.tid; i < b.n; i += b.B)
-            b.xs[padidx((uint32_t)(GUARD + i))] =
-                load_sample(base, (u64)i * (u64)ch + (u64)c_only, p.cbytes, p.bps, aligned);
+        done = groups << 3;
+    } else if (p.cbytes == 3 && (((uintptr_t)base) & 3) == 0) {
+        /* 24-bit: four samples per three 32-bit loads */
+        const int groups = total >> 2;
+        const uint32_t *src = (const uint32_t *)base;
+        for (int g = b.tid; g < groups; g += b.B) {
+            const uint32_t w0 = src[3 * g], w1 = src[3 * g + 1], w2 = src[3 * g + 2];
+            put(4 * g, (int32_t)(w0 << 8) >> 8);
+            put(4 * g + 1, (int32_t)(((w0 >> 24) | (w1 << 8)) << 8) >> 8);
+            put(4 * g + 2, (int32_t)(((w1 >> 16) | (w2 << 16)) << 8) >> 8);
+            put(4 * g + 3, (int32_t)w2 >> 8);
+        }
+        done = groups << 2;
     }
+    for (int sidx = done + b.tid; sidx < total; sidx += b.B) put(sidx, load_sample(base, (u64)sidx, p.cbytes, p.bps, aligned));
     __syncthreads();
 }
 
@@ -629,6 +654,25 @@ __device__ void quantize_order(Blk &b, int m, int precision)
  * encoder.py:537-548).  History window in registers, coefficients broadcast from shared
  * memory, 32-bit accumulation whenever sum|q| * 2^(bps-1) proves it exact.                 */
 
+/* Generic, rolled evaluation of one order for one thread's samples: 64-bit accumulation, window
+ * read from shared memory, warm-up and end-of-block masking.  Used by the few threads at the
+ * edges of a block and for orders whose coefficients are too large for 32-bit sums; kept out of
+ * line so that the unrolled fast path below stays small (instruction cache). */
+__device__ __noinline__ u64 lpc_error_slow(const int32_t *x, const int32_t *q, int i0, int n, int m, int shift)
+{
+    u64 tot = 0;
+    for (int e = 0; e < E; e++) {
+        const int i = i0 + e;
+        if (i >= m && i < n) {
+            i64 acc = 0;
+            for (int j = 0; j < m; j++) acc += (i64)x[padidx((uint32_t)(GUARD + i - 1 - j))] * (i64)q[j];
+            const i64 r = (i64)x[padidx((uint32_t)(GUARD + i))] - (acc >> shift);
+            tot += (u64)(r < 0 ? -r : r);
+        }
+    }
+    return tot;
+}
+
 template <int LMAX>
 __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 {
@@ -638,66 +682,36 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
     u64 lane_tot = 0; /* lane m-1 of every warp keeps the warp's running total of order m */
     for (int tile = 0; tile < b.ntiles; tile++) {
         const int i0 = (tile * b.B + b.tid) * E;
-        int h[LMAX + E];
-        if (i0 < n) {
-#pragma unroll
-            for (int j = 0; j < LMAX + E; j++) h[j] = x[padidx((uint32_t)(GUARD + i0 - LMAX + j))];
-        } else {
-#pragma unroll
-            for (int j = 0; j < LMAX + E; j++) h[j] = 0;
-        }
         const bool interior = i0 >= LMAX && i0 + E <= n; /* no warm-up or end-of-block masking */
+        int h[LMAX + E];
+#pragma unroll
+        for (int j = 0; j < LMAX + E; j++) h[j] = interior ? x[padidx((uint32_t)(GUARD + i0 - LMAX + j))] : 0;
 #pragma unroll
         for (int m = 1; m <= LMAX; m++) {
             if (m <= L && sh.qncoef[m - 1] != 0) {
                 const int shift = sh.qshift[m - 1];
+                const int32_t *q = b.qc + (m - 1) * b.ldL;
+                const bool small = ((u64)sh.qabs[m - 1] << (b.p.bps - 1)) <= lim32; /* 32-bit sums are exact */
                 u64 tot = 0;
-                if (((u64)sh.qabs[m - 1] << (b.p.bps - 1)) <= lim32) {
+                if (small && interior) {
                     int acc[E];
 #pragma unroll
                     for (int e = 0; e < E; e++) acc[e] = 0;
 #pragma unroll
                     for (int j = 0; j < m; j++) {
-                        const int cj = b.qc[(m - 1) * b.ldL + j];
+                        const int cj = q[j];
 #pragma unroll
                         for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
                     }
-                    if (interior) {
-                        /* |r| < 2^31 each: pairs fit 32 bits */
+                    /* |r| < 2^31 each: pairs fit 32 bits */
 #pragma unroll
-                        for (int e = 0; e < E; e += 2) {
-                            const int r0 = h[LMAX + e] - (acc[e] >> shift);
-                            const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
-                            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E; e++) {
-                            const int i = i0 + e;
-                            if (i >= m && i < n) {
-                                const int r = h[LMAX + e] - (acc[e] >> shift);
-                                tot += (u64)(uint32_t)(r < 0 ? -r : r);
-                            }
-                        }
+                    for (int e = 0; e < E; e += 2) {
+                        const int r0 = h[LMAX + e] - (acc[e] >> shift);
+                        const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
+                        tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
                     }
-                } else {
-                    i64 acc[E];
-#pragma unroll
-                    for (int e = 0; e < E; e++) acc[e] = 0;
-#pragma unroll
-                    for (int j = 0; j < m; j++) {
-                        const i64 cj = b.qc[(m - 1) * b.ldL + j];
-#pragma unroll
-                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
-                    }
-#pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        const int i = i0 + e;
-                        if (i >= m && i < n) {
-                            const i64 r = (i64)h[LMAX + e] - (acc[e] >> shift);
-                            tot += (u64)(r < 0 ? -r : r);
-                        }
-                    }
+                } else if (i0 < n) {
+                    tot = lpc_error_slow(x, q, i0, n, m, shift);
                 }
                 tot = warp_sum_u64(tot);
                 if (b.lane == m - 1) lane_tot += tot;
@@ -719,7 +733,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
  * running sum cum[g] = sum of res[0 .. g*E) that the Rice search reads partition sums from */
 
 template <int LMAX>
-__device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
+__device__ __noinline__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
 {
     const int n = b.n;
     u64 base = 0;
@@ -870,47 +884,40 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
         }
     }
     __syncthreads();
-    /* sum over samples of (u >> k) for every candidate order (rice_size, encoder.py:756-760) */
-    u64 acc[MAX_CAND];
+    /* sum over samples of (u >> k) for every candidate order (rice_size, encoder.py:756-760);
+     * u >> k < 2^29 for bps <= 24, so a thread's tile sum fits 32 bits */
+    u64 lane_q = 0;
+#pragma unroll 1
+    for (int ci = 0; ci < ncand; ci++) {
+        const uint32_t o = sh.cand_o[ci];
+        const uint32_t psz = (uint32_t)n >> o;
+        const uint32_t magic = sh.cand_magic[ci];
+        const uint8_t *kk = b.kall + (1u << o);
+        u64 acc = 0;
+#pragma unroll 1
+        for (int tile = 0; tile < b.ntiles; tile++) {
+            const int i0 = (tile * b.B + b.tid) * E;
+            if (i0 < n) {
+                uint32_t u[E];
 #pragma unroll
-    for (int ci = 0; ci < MAX_CAND; ci++) acc[ci] = 0;
-    for (int tile = 0; tile < b.ntiles; tile++) {
-        const int i0 = (tile * b.B + b.tid) * E;
-        if (i0 < n) {
-            uint32_t u[E];
+                for (int e = 0; e < E; e++) u[e] = b.res[padidx((uint32_t)(i0 + e))];
+                const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
+                const uint32_t bnd = (p0 + 1) * psz;
+                uint32_t t32 = 0;
+                if ((uint32_t)(i0 + E) <= bnd) { /* the run lies in one partition (the usual case) */
+                    const uint32_t k0 = kk[p0];
 #pragma unroll
-            for (int e = 0; e < E; e++) u[e] = b.res[padidx((uint32_t)(i0 + e))];
+                    for (int e = 0; e < E; e++) t32 += u[e] >> k0;
+                } else {
 #pragma unroll
-            for (int ci = 0; ci < MAX_CAND; ci++) {
-                if (ci < ncand) {
-                    const uint32_t o = sh.cand_o[ci];
-                    const uint32_t psz = (uint32_t)n >> o;
-                    const uint32_t magic = sh.cand_magic[ci];
-                    const uint8_t *kk = b.kall + (1u << o);
-                    if (psz >= (uint32_t)E) {
-                        const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
-                        const uint32_t bnd = (p0 + 1) * psz;
-                        const uint32_t k0 = kk[p0];
-                        const uint32_t k1 = (p0 + 1 < (1u << o)) ? kk[p0 + 1] : 0u;
-#pragma unroll
-                        for (int e = 0; e < E; e++) acc[ci] += u[e] >> ((uint32_t)(i0 + e) < bnd ? k0 : k1);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E; e++) {
-                            if (i0 + e < n) acc[ci] += u[e] >> kk[fast_div((uint32_t)(i0 + e), psz, magic)];
-                        }
-                    }
+                    for (int e = 0; e < E; e++)
+                        if (i0 + e < n) t32 += u[e] >> kk[fast_div((uint32_t)(i0 + e), psz, magic)];
                 }
+                acc += t32;
             }
         }
-    }
-    u64 lane_q = 0;
-#pragma unroll
-    for (int ci = 0; ci < MAX_CAND; ci++) {
-        if (ci < ncand) {
-            const u64 t = warp_sum_u64(acc[ci]);
-            if (b.lane == ci) lane_q = t;
-        }
+        const u64 t = warp_sum_u64(acc);
+        if (b.lane == ci) lane_q = t;
     }
     if (b.lane < MAX_CAND) b.red[b.warp * RED_STRIDE + b.lane] = lane_q;
     __syncthreads();
@@ -965,19 +972,93 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t bb)
     return r;
 }
 
+/* phase 2, deferred: byte offset of this frame = sum of the sizes of all frames in front of it.
+ * Decoupled look-back, one warp, 32 predecessors per probe: sizes are summed backwards until a
+ * frame that already knows its own inclusive prefix is met. */
+__device__ __noinline__ void resolve_offset(Blk &b)
+{
+    Shared &sh = b.sh;
+    const EncParams &p = b.p;
+    const uint32_t f = sh.frame;
+    if (p.slot_stride) {
+        if (b.tid == 0) sh.frame_off = (u64)f * p.slot_stride;
+    } else if (b.warp == 0) {
+        const u64 mine = (u64)sh.frame_bytes;
+        u64 excl = 0;
+        bool failed = false;
+        if (f > 0) {
+            int64_t j = (int64_t)f - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const int64_t idx = j - b.lane;
+                u64 s = LB_PREFIX; /* before frame 0: an empty prefix */
+                if (idx >= 0) s = *(volatile u64 *)&p.lb_state[idx];
+                const uint32_t flag = (uint32_t)(s >> 62);
+                const unsigned has_prefix = __ballot_sync(FULL, flag == 2);
+                const unsigned invalid = __ballot_sync(FULL, flag == 0);
+                const int first_prefix = has_prefix ? __ffs((int)has_prefix) - 1 : 32;
+                const unsigned need = first_prefix == 32 ? FULL : ((2u << first_prefix) - 1u);
+                if (invalid & need) { /* a predecessor has not published yet */
+                    if (++spins > (1u << 22)) { failed = true; break; }
+                    __nanosleep(64);
+                    continue;
+                }
+                u64 v = (b.lane <= first_prefix) ? (s & LB_VALUE) : 0ull;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+                excl += v;
+                if (first_prefix < 32) break;
+                j -= 32;
+            }
+            if (b.lane == 0) atomicExch(&p.lb_state[f], LB_PREFIX | ((excl + mine) & LB_VALUE));
+        }
+        if (b.lane == 0) {
+            sh.frame_off = excl;
+            p.frame_off[f] = excl;
+            if (f == p.n_frames - 1) p.frame_off[p.n_frames] = excl + mine;
+            if (failed) set_status(b, FLACB_E_INTERNAL);
+        }
+    }
+    __syncthreads();
+    if (b.tid == 0) {
+        const u64 lim = p.slot_stride ? p.slot_stride : p.out_cap - (sh.frame_off < p.out_cap ? sh.frame_off : p.out_cap);
+        sh.writable = (u64)sh.frame_bytes <= lim && (p.slot_stride == 0 || sh.frame_off + sh.frame_bytes <= p.out_cap) &&
+                      sh.status != FLACB_E_INTERNAL;
+        if (!sh.writable && sh.status == 0) sh.status = FLACB_E_NOSPACE;
+        sh.have_off = 1;
+    }
+    __syncthreads();
+}
+
 /* Flush the first `nbytes` bytes of the staging window to the frame in HBM and fold them into
  * the frame CRC-16 (crc.py:25-30): every thread takes a 64-byte slice, and because the CRC has
  * zero init and no final xor, crc(A || B) = crc(A) * x^(8|B|) + crc(B), so a slice's CRC times
  * x^(8 * bytes behind it) can simply be xor-ed into the frame's.  Then the window is rebased at
  * word `wend` (the partial word, if any, moves to the front). */
-__device__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
+__device__ __noinline__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
 {
     Shared &sh = b.sh;
+    if (!sh.have_off) resolve_offset(b); /* block-uniform */
     const uint32_t byte0 = sh.wbase * 4u; /* frame-relative */
-    if (sh.writable) {
+    if (sh.writable && nbytes) {
+        /* staging words hold the stream MSB first; memory wants those bytes in order.  Aligned
+         * 32-bit stores for the body, single bytes in front of / behind it. */
         uint8_t *dst = b.p.out + sh.frame_off + byte0;
-        for (uint32_t idx = (uint32_t)b.tid; idx < nbytes; idx += (uint32_t)b.B)
-            dst[idx] = (uint8_t)(b.stg[idx >> 2] >> (24u - 8u * (idx & 3u)));
+        uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
+        if (head > nbytes) head = nbytes;
+        const uint32_t nq = (nbytes - head) >> 2;
+        const uint32_t tail0 = head + nq * 4u;
+        for (uint32_t idx = (uint32_t)b.tid; idx < head + (nbytes - tail0); idx += (uint32_t)b.B) {
+            const uint32_t i = idx < head ? idx : tail0 + (idx - head);
+            dst[i] = (uint8_t)(b.stg[i >> 2] >> (24u - 8u * (i & 3u)));
+        }
+        uint32_t *dstw = (uint32_t *)(dst + head);
+        const uint32_t r = head & 3u; /* byte offset of every aligned word inside the staging words */
+        for (uint32_t q = (uint32_t)b.tid; q < nq; q += (uint32_t)b.B) {
+            const uint32_t j = (head + 4u * q) >> 2;
+            const uint32_t s0 = __byte_perm(b.stg[j], 0, 0x0123), s1 = __byte_perm(b.stg[j + 1], 0, 0x0123);
+            dstw[q] = r == 0 ? s0 : __funnelshift_r(s0, s1, 8u * r);
+        }
     }
     const uint32_t nslices = (nbytes + CRC_SLICE - 1) / CRC_SLICE;
     for (uint32_t sl = (uint32_t)b.tid; sl < nslices; sl += (uint32_t)b.B) {
@@ -994,8 +1075,13 @@ __device__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
     }
     const uint32_t carry_idx = wend - sh.wbase;
     const uint32_t carry = carry_idx <= b.stg_words ? b.stg[carry_idx] : 0u;
+    /* nothing beyond the word the bit cursor is in has been written */
+    uint32_t used = (sh.pos >> 5) - sh.wbase;
+    if (used < (nbytes + 3u) / 4u) used = (nbytes + 3u) / 4u; /* a tile wider than the window is flushed mid-way */
+    used += 2u;
+    if (used > b.stg_words + 4u) used = b.stg_words + 4u;
     __syncthreads();
-    for (int idx = b.tid; idx < (int)b.stg_words + 4; idx += b.B) b.stg[idx] = idx == 0 ? carry : 0u;
+    for (uint32_t idx = (uint32_t)b.tid; idx < used; idx += (uint32_t)b.B) b.stg[idx] = idx == 0 ? carry : 0u;
     if (b.tid == 0) sh.wbase = wend;
     __syncthreads();
 }
@@ -1332,7 +1418,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.flat_lo = tail_frame ? p.flat_tail_lo : p.flat_full_lo;
     b.flat_hi = tail_frame ? p.flat_tail_hi : p.flat_full_hi;
 
-    const SmemLayout lay = make_layout(p.block_size, p.channels, p.bps, p.rmax, p.L, b.B, p.all_planes);
+    const SmemLayout &lay = p.lay;
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
     b.res = (uint32_t *)(smem + lay.res);
@@ -1366,53 +1452,12 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         p.frame_bytes[f] = sh.frame_bytes;
     }
     __syncthreads();
-    if (p.slot_stride) {
-        if (b.tid == 0) sh.frame_off = (u64)f * p.slot_stride;
-    } else if (b.warp == 0) {
-        /* decoupled look-back, one warp: 32 predecessors per probe */
-        const u64 mine = (u64)sh.frame_bytes;
-        u64 excl = 0;
-        bool failed = false;
-        if (f > 0) {
-            if (b.lane == 0) atomicExch(&p.lb_state[f], LB_AGG | mine);
-            int64_t j = (int64_t)f - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const int64_t idx = j - b.lane;
-                u64 s = LB_PREFIX; /* before frame 0: an empty prefix */
-                if (idx >= 0) s = *(volatile u64 *)&p.lb_state[idx];
-                const uint32_t flag = (uint32_t)(s >> 62);
-                const unsigned has_prefix = __ballot_sync(FULL, flag == 2);
-                const unsigned invalid = __ballot_sync(FULL, flag == 0);
-                const int first_prefix = has_prefix ? __ffs((int)has_prefix) - 1 : 32;
-                const unsigned need = first_prefix == 32 ? FULL : ((2u << first_prefix) - 1u);
-                if (invalid & need) { /* a predecessor has not published yet */
-                    if (++spins > (1u << 22)) { failed = true; break; }
-                    __nanosleep(64);
-                    continue;
-                }
-                u64 v = (b.lane <= first_prefix) ? (s & LB_VALUE) : 0ull;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-                excl += v;
-                if (first_prefix < 32) break;
-                j -= 32;
-            }
-        }
-        if (b.lane == 0) {
-            atomicExch(&p.lb_state[f], LB_PREFIX | ((excl + mine) & LB_VALUE));
-            sh.frame_off = excl;
-            p.frame_off[f] = excl;
-            if (f == p.n_frames - 1) p.frame_off[p.n_frames] = excl + mine;
-            if (failed) set_status(b, FLACB_E_INTERNAL);
-        }
-    }
-    __syncthreads();
+    /* The size is published at once; the frame's own offset is only looked up when the first
+     * bytes leave shared memory (flush_window -> resolve_offset), by which time the frames in
+     * front have long published theirs: nobody waits for a slower predecessor's analysis. */
     if (b.tid == 0) {
-        const u64 lim = p.slot_stride ? p.slot_stride : p.out_cap - (sh.frame_off < p.out_cap ? sh.frame_off : p.out_cap);
-        sh.writable = (u64)sh.frame_bytes <= lim && (p.slot_stride == 0 || sh.frame_off + sh.frame_bytes <= p.out_cap) &&
-                      sh.status != FLACB_E_INTERNAL;
-        if (!sh.writable && sh.status == 0) sh.status = FLACB_E_NOSPACE;
+        sh.have_off = 0;
+        if (!p.slot_stride) atomicExch(&p.lb_state[f], f == 0 ? (LB_PREFIX | (u64)sh.frame_bytes) : (LB_AGG | (u64)sh.frame_bytes));
     }
     for (int idx = b.tid; idx < (int)b.stg_words + 4; idx += b.B) b.stg[idx] = 0;
     __syncthreads();

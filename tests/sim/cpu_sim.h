@@ -22,6 +22,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __constant__
 #define __launch_bounds__(...)
@@ -29,6 +30,7 @@
 
 struct sim_dim3 { unsigned x, y, z; };
 struct double2 { double x, y; };
+struct uint4 { unsigned x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
 
 namespace sim {
@@ -209,6 +211,11 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
     unsigned r = 0;
     for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
     return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
+{
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)(v >> (shift & 31));
 }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __clzll(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }

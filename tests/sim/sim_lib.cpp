@@ -76,6 +76,7 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     const int B = threads_override ? threads_override : shape.threads;
     const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, shape.all_planes);
     p.all_planes = shape.all_planes;
+    p.lay = lay;
 
     std::vector<uint32_t> frame_bytes(n_frames);
     std::vector<u64> frame_off(n_frames + 1, 0);
