@@ -131,7 +131,7 @@ struct BitReader {
     int avail;
     bool eof;
 
-    __device__ void init(const uint8_t *s, u64 length, u64 byte_pos)
+    __device__ __forceinline__ void init(const uint8_t *s, u64 length, u64 byte_pos)
     {
         p = s, len = length, next = byte_pos, buf = 0, avail = 0, eof = false;
     }
@@ -211,7 +211,7 @@ struct BitReader {
 
 /* decoder.py:133-185 get_frame_header and the field decoders :188-262.  Returns the status the
  * reference raises, FLACB_E_EOF when the stream ends inside the header. */
-__device__ int parse_frame_header(BitReader &g, int si_bits, Candidate &c)
+__device__ __forceinline__ int parse_frame_header(BitReader &g, int si_bits, Candidate &c)
 {
     const uint32_t sync = g.read(15);
     if (g.eof) return FLACB_E_EOF;
@@ -307,7 +307,7 @@ struct History { /* last 32 reconstructed samples, circular */
 
 /* decoder.py:358-421 get_residual with the prediction of decoder.py:493-498 applied on the fly:
  * out[i] = residual + (sum_j out[i-1-j] * coef[j] >> shift) */
-__device__ int decode_residual(BitReader &g, int bs, int order, const int32_t *coef, int shift, History &hist,
+__device__ __forceinline__ int decode_residual(BitReader &g, int bs, int order, const int32_t *coef, int shift, History &hist,
                                int32_t *out, bool is_fixed)
 {
     i64 x1 = 0, x2 = 0, x3 = 0, x4 = 0; /* out[pos-1] .. out[pos-4] for the fixed predictors */
@@ -368,7 +368,7 @@ __device__ int decode_residual(BitReader &g, int bs, int order, const int32_t *c
 }
 
 /* decoder.py:267-355 get_subframe + :453-498 decode_subframe */
-__device__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *out)
+__device__ __forceinline__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *out)
 {
     const uint32_t padbit = g.read(1);
     if (g.eof) return FLACB_E_EOF;

@@ -60,6 +60,10 @@ constexpr int CRC_SLICE = 64;   /* bytes per thread in the parallel CRC-16 */
 constexpr int XPOW_HI = 8192;   /* x^(8*256*h) table entries: frames up to 2 MiB */
 constexpr unsigned FULL = 0xffffffffu;
 
+/* Helpers used from several places stay inline: an out-of-line call forces the per-thread block
+ * state (Blk) into local memory, which cost 40 % on the fixed-predictor path when measured. */
+#define FLACB_OUTLINE
+
 /* look-back state flags (top two bits of a 64-bit word, value below) */
 constexpr u64 LB_AGG = 1ull << 62;
 constexpr u64 LB_PREFIX = 2ull << 62;
@@ -654,25 +658,6 @@ __device__ void quantize_order(Blk &b, int m, int precision)
  * encoder.py:537-548).  History window in registers, coefficients broadcast from shared
  * memory, 32-bit accumulation whenever sum|q| * 2^(bps-1) proves it exact.                 */
 
-/* Generic, rolled evaluation of one order for one thread's samples: 64-bit accumulation, window
- * read from shared memory, warm-up and end-of-block masking.  Used by the few threads at the
- * edges of a block and for orders whose coefficients are too large for 32-bit sums; kept out of
- * line so that the unrolled fast path below stays small (instruction cache). */
-__device__ __noinline__ u64 lpc_error_slow(const int32_t *x, const int32_t *q, int i0, int n, int m, int shift)
-{
-    u64 tot = 0;
-    for (int e = 0; e < E; e++) {
-        const int i = i0 + e;
-        if (i >= m && i < n) {
-            i64 acc = 0;
-            for (int j = 0; j < m; j++) acc += (i64)x[padidx((uint32_t)(GUARD + i - 1 - j))] * (i64)q[j];
-            const i64 r = (i64)x[padidx((uint32_t)(GUARD + i))] - (acc >> shift);
-            tot += (u64)(r < 0 ? -r : r);
-        }
-    }
-    return tot;
-}
-
 template <int LMAX>
 __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 {
@@ -685,7 +670,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
         const bool interior = i0 >= LMAX && i0 + E <= n; /* no warm-up or end-of-block masking */
         int h[LMAX + E];
 #pragma unroll
-        for (int j = 0; j < LMAX + E; j++) h[j] = interior ? x[padidx((uint32_t)(GUARD + i0 - LMAX + j))] : 0;
+        for (int j = 0; j < LMAX + E; j++) h[j] = i0 < n ? x[padidx((uint32_t)(GUARD + i0 - LMAX + j))] : 0;
 #pragma unroll
         for (int m = 1; m <= LMAX; m++) {
             if (m <= L && sh.qncoef[m - 1] != 0) {
@@ -693,7 +678,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
                 const int32_t *q = b.qc + (m - 1) * b.ldL;
                 const bool small = ((u64)sh.qabs[m - 1] << (b.p.bps - 1)) <= lim32; /* 32-bit sums are exact */
                 u64 tot = 0;
-                if (small && interior) {
+                if (small) {
                     int acc[E];
 #pragma unroll
                     for (int e = 0; e < E; e++) acc[e] = 0;
@@ -703,15 +688,43 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
 #pragma unroll
                         for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
                     }
-                    /* |r| < 2^31 each: pairs fit 32 bits */
+                    if (interior) {
+                        /* |r| < 2^31 each: pairs fit 32 bits */
 #pragma unroll
-                    for (int e = 0; e < E; e += 2) {
-                        const int r0 = h[LMAX + e] - (acc[e] >> shift);
-                        const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
-                        tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
+                        for (int e = 0; e < E; e += 2) {
+                            const int r0 = h[LMAX + e] - (acc[e] >> shift);
+                            const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
+                            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; e++) {
+                            const int i = i0 + e;
+                            if (i >= m && i < n) {
+                                const int r = h[LMAX + e] - (acc[e] >> shift);
+                                tot += (u64)(uint32_t)(r < 0 ? -r : r);
+                            }
+                        }
                     }
-                } else if (i0 < n) {
-                    tot = lpc_error_slow(x, q, i0, n, m, shift);
+                } else {
+                    /* coefficients too large for 32-bit sums (24-bit input, high precisions) */
+                    i64 acc[E];
+#pragma unroll
+                    for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+                    for (int j = 0; j < m; j++) {
+                        const i64 cj = q[j];
+#pragma unroll
+                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const int i = i0 + e;
+                        if (i >= m && i < n) {
+                            const i64 r = (i64)h[LMAX + e] - (acc[e] >> shift);
+                            tot += (u64)(r < 0 ? -r : r);
+                        }
+                    }
                 }
                 tot = warp_sum_u64(tot);
                 if (b.lane == m - 1) lane_tot += tot;
@@ -733,7 +746,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
  * running sum cum[g] = sum of res[0 .. g*E) that the Rice search reads partition sums from */
 
 template <int LMAX>
-__device__ __noinline__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
+__device__ FLACB_OUTLINE void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
 {
     const int n = b.n;
     u64 base = 0;
@@ -975,7 +988,7 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t bb)
 /* phase 2, deferred: byte offset of this frame = sum of the sizes of all frames in front of it.
  * Decoupled look-back, one warp, 32 predecessors per probe: sizes are summed backwards until a
  * frame that already knows its own inclusive prefix is met. */
-__device__ __noinline__ void resolve_offset(Blk &b)
+__device__ FLACB_OUTLINE void resolve_offset(Blk &b)
 {
     Shared &sh = b.sh;
     const EncParams &p = b.p;
@@ -1035,7 +1048,7 @@ __device__ __noinline__ void resolve_offset(Blk &b)
  * zero init and no final xor, crc(A || B) = crc(A) * x^(8|B|) + crc(B), so a slice's CRC times
  * x^(8 * bytes behind it) can simply be xor-ed into the frame's.  Then the window is rebased at
  * word `wend` (the partial word, if any, moves to the front). */
-__device__ __noinline__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
+__device__ FLACB_OUTLINE void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
 {
     Shared &sh = b.sh;
     if (!sh.have_off) resolve_offset(b); /* block-uniform */
