@@ -307,7 +307,7 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
     auto layout_total = [&](int threads, int all_planes) {
         return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
     };
-    plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total);
+    plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total, a.max_lpc_order > 0);
     if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
     if (const char *e = getenv("FLACB200_SHAPE")) { /* tuning knob: "threads,all_planes,variant" */
         int t = 0, ap = 1, v = 0;
@@ -701,7 +701,7 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     if ((rc = c->d_frames.ensure((tmp_samples + 16) * 4))) return rc;
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
-    decode_frames_kernel<<<(unsigned)((n_cand + DECODE_WARPS - 1) / DECODE_WARPS), 32 * DECODE_WARPS, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
+    decode_frames_kernel<<<(unsigned)((n_cand + 31) / 32), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
                                                                                d_tmpoff, d_tmp, check_crc8);
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;

@@ -294,7 +294,15 @@ __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Can
 
 /* ---- D3 ------------------------------------------------------------------------------ */
 
-struct History { /* last 32 reconstructed samples, circular */
+/* One LANE per candidate frame, 32 frames per warp.  Rice parsing is a serial, data dependent
+ * walk through the bit stream; 32 lanes walking 32 different frames with ordinary nested loops
+ * diverge at every code and end up serialised (the first version: 30x slower).  So the frame
+ * decode is written as a state machine: every lane is in one of a few states and a warp-wide
+ * loop advances all lanes by one step per iteration.  Practically all iterations find all lanes
+ * in ST_RICE (one Rice code per step, at most one refill per step), so the warp stays
+ * converged; header fields, warm-up samples, partition parameters are rare steps. */
+
+struct History { /* last 32 reconstructed samples, circular (LPC subframes) */
     i64 h[32];
     int head;
     __device__ __forceinline__ void push(i64 v)
@@ -305,186 +313,306 @@ struct History { /* last 32 reconstructed samples, circular */
     __device__ __forceinline__ i64 back(int j) const { return h[(head - 1 - j) & 31]; } /* x[i-1-j] */
 };
 
-/* decoder.py:358-421 get_residual with the prediction of decoder.py:493-498 applied on the fly:
- * out[i] = residual + (sum_j out[i-1-j] * coef[j] >> shift) */
-__device__ __forceinline__ int decode_residual(BitReader &g, int bs, int order, const int32_t *coef, int shift, History &hist,
-                               int32_t *out, bool is_fixed)
+enum {
+    ST_SUB_HDR = 0, /* subframe header byte, wasted bits (decoder.py:318-355) */
+    ST_WASTED,      /* unary wasted-bits count in progress */
+    ST_CONST,       /* constant subframe value */
+    ST_VERBATIM,    /* one verbatim sample per step */
+    ST_WARMUP,      /* one warm-up sample per step */
+    ST_LPC_HDR,     /* precision, shift */
+    ST_COEF,        /* one coefficient per step */
+    ST_RES_HDR,     /* coding method, partition order (decoder.py:358-384) */
+    ST_PART_HDR,    /* Rice parameter / escape size of the next partition */
+    ST_RICE,        /* one Rice coded residual per step (decoder.py:414-421) */
+    ST_ESCAPED,     /* one escaped (raw) residual per step (decoder.py:404-407) */
+    ST_FRAME_END,   /* padding + CRC-16 */
+    ST_DONE
+};
+
+struct LaneState {
+    BitReader g;
+    int state, status;
+    int ch, nch, chcode, bs, sample_size; /* frame */
+    int ss, type, order, shift, precision; /* subframe */
+    int pos, idx;                         /* sample position in the subframe; warm-up / coef index */
+    int method, porder, parts_left, part_left, k, esc_size;
+    u64 cnt;                              /* zeros of an unfinished unary run */
+    i64 x1, x2, x3, x4;                   /* last four samples (fixed predictors, common.py:15-21) */
+    int32_t *out;                         /* this channel's plane in the scratch area */
+};
+
+__device__ __forceinline__ void lane_fail(LaneState &st, int status)
 {
-    i64 x1 = 0, x2 = 0, x3 = 0, x4 = 0; /* out[pos-1] .. out[pos-4] for the fixed predictors */
-    if (is_fixed) {
-        if (order >= 1) x1 = hist.back(0);
-        if (order >= 2) x2 = hist.back(1);
-        if (order >= 3) x3 = hist.back(2);
-        if (order >= 4) x4 = hist.back(3);
-    }
-    const uint32_t m = g.read(2);
-    if (g.eof) return FLACB_E_EOF;
-    if (m > 1) return FLACB_E_VALUE; /* RiceCodingMethod(x) */
-    const int method = m == 0 ? 4 : 5;
-    const int porder = (int)g.read(4);
-    if (g.eof) return FLACB_E_EOF;
-    const int nparts = 1 << porder;
-    if (bs % nparts != 0) return FLACB_E_ASSERT;
-    if (!((bs >> porder) > order)) return FLACB_E_ASSERT;
-    int pos = order;
-    for (int p = 0; p < nparts; p++) {
-        const int cnt = p == 0 ? (bs >> porder) - order : (bs >> porder);
-        const int k = (int)g.read(method);
-        if (g.eof) return FLACB_E_EOF;
-        const bool escaped = k == (1 << method) - 1; /* decoder.py:404-407 */
-        int size = 0;
-        if (escaped) {
-            size = (int)g.read(5);
-            if (g.eof) return FLACB_E_EOF;
-            if (size == 0 && cnt > 0) return FLACB_E_VALUE; /* sint(0): negative shift count */
-        }
-        for (int i = 0; i < cnt; i++) {
-            i64 r;
-            if (escaped) r = g.read_signed(size);
-            else {
-                const u64 msb = g.unary();
-                const u64 lsb = g.read(k);
-                const u64 u = (msb << k) | lsb;
-                r = (i64)(u >> 1) ^ -(i64)(u & 1); /* utils.py:87-88 zigzag_decode */
-            }
-            if (g.eof) return FLACB_E_EOF;
-            i64 v;
-            if (is_fixed) {
-                /* fixed predictors (common.py:15-21) on the last four samples, kept in registers */
-                const i64 pred = order == 0 ? 0 : order == 1 ? x1 : order == 2 ? 2 * x1 - x2
-                                 : order == 3 ? 3 * x1 - 3 * x2 + x3 : 4 * x1 - 6 * x2 + 4 * x3 - x4;
-                v = r + pred;
-                x4 = x3, x3 = x2, x2 = x1, x1 = v;
-            } else {
-                i64 acc = 0;
-                for (int j = 0; j < order; j++) acc += hist.back(j) * (i64)coef[j];
-                v = r + (acc >> shift);
-                hist.push(v);
-            }
-            out[pos++] = (int32_t)v;
-        }
-    }
-    return FLACB_OK;
+    st.status = status;
+    st.state = ST_DONE;
 }
 
-/* decoder.py:267-355 get_subframe + :453-498 decode_subframe */
-__device__ __forceinline__ int decode_subframe(BitReader &g, int bs, int sample_size, int32_t *out)
+/* word-wise refill: keeps 33..64 bits buffered; bytes only in front of the first aligned word and
+ * behind the last one.  At most one load per call on the fast path. */
+__device__ __forceinline__ void lane_refill(BitReader &g)
 {
-    const uint32_t padbit = g.read(1);
-    if (g.eof) return FLACB_E_EOF;
-    if (padbit != 0) return FLACB_E_ASSERT;
-    const int type = (int)g.read(6);
-    if (g.eof) return FLACB_E_EOF;
-    if (!(type <= 1 || (type >= 8 && type <= 12) || type >= 32)) return FLACB_E_ASSERT;
-    int wasted = 0;
-    const uint32_t wflag = g.read(1);
-    if (g.eof) return FLACB_E_EOF;
-    if (wflag) { /* decoder.py:346-355: counts the zeros (one less than the format says) and
-                    never shifts the samples back; reproduced */
-        wasted = (int)g.unary();
-        if (g.eof) return FLACB_E_EOF;
+    if (g.avail <= 32 && g.next + 4 <= g.len && (((uintptr_t)(g.p + g.next)) & 3) == 0) {
+        const uint32_t w = *(const uint32_t *)(g.p + g.next);
+        g.buf |= (u64)__byte_perm(w, 0, 0x0123) << (32 - g.avail);
+        g.avail += 32;
+        g.next += 4;
+    } else if (g.avail <= 32) {
+        g.refill(); /* ends of the stream, unaligned start */
     }
-    const int ss = sample_size - wasted;
-    if (type == 0) { /* constant */
-        if (ss <= 0 || ss > 40) return FLACB_E_VALUE;
-        const i64 v = g.read_signed(ss);
-        if (g.eof) return FLACB_E_EOF;
-        for (int i = 0; i < bs; i++) out[i] = (int32_t)v;
-        return FLACB_OK;
-    }
-    if (type == 1) { /* verbatim */
-        if (ss <= 0 || ss > 40) return FLACB_E_VALUE;
-        for (int i = 0; i < bs; i++) {
-            out[i] = (int32_t)g.read_signed(ss);
-            if (g.eof) return FLACB_E_EOF;
-        }
-        return FLACB_OK;
-    }
-    History hist;
-    hist.head = 0;
-    int32_t coef[FLACB_MAX_LPC];
-    int order, shift = 0;
-    if (type <= 12) { /* fixed, common.py:15-21 */
-        order = type & 7;
-        const int32_t fc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-        for (int j = 0; j < 4; j++) coef[j] = fc[order][j];
-    } else order = (type & 31) + 1;
-    if (ss <= 0 || ss > 40) {
-        if (order > 0) return FLACB_E_VALUE;
-    }
-    for (int i = 0; i < order; i++) {
-        if (i >= bs) return FLACB_E_ASSERT; /* warm-up longer than the block */
-        const i64 v = g.read_signed(ss);
-        if (g.eof) return FLACB_E_EOF;
+}
+
+__device__ __forceinline__ void lane_store(LaneState &st, History &hist, const int32_t *coef, i64 r)
+{
+    /* prediction restore of decoder.py:493-498 on the fly */
+    i64 v;
+    if (st.type <= 12) {
+        const int o = st.order;
+        const i64 pred = o == 0 ? 0 : o == 1 ? st.x1 : o == 2 ? 2 * st.x1 - st.x2
+                         : o == 3 ? 3 * st.x1 - 3 * st.x2 + st.x3 : 4 * st.x1 - 6 * st.x2 + 4 * st.x3 - st.x4;
+        v = r + pred;
+    } else {
+        i64 acc = 0;
+        for (int j = 0; j < st.order; j++) acc += hist.back(j) * (i64)coef[j];
+        v = r + (acc >> (st.shift < 0 ? 0 : st.shift));
         hist.push(v);
-        out[i] = (int32_t)v;
     }
-    if (type >= 32) {
-        int precision = (int)g.read(4);
-        if (g.eof) return FLACB_E_EOF;
-        if (precision == 15) return FLACB_E_ASSERT;
-        precision += 1;
-        shift = (int)g.read_signed(5);
-        for (int i = 0; i < order; i++) coef[i] = (int32_t)g.read_signed(precision);
-        if (g.eof) return FLACB_E_EOF;
-        /* a negative shift only fails once the prediction runs (decoder.py:497); the residual is
-         * parsed first */
-    }
-    const int rc = decode_residual(g, bs, order, coef, shift < 0 ? 0 : shift, hist, out, type <= 12);
-    if (rc) return rc;
-    if (shift < 0) return FLACB_E_VALUE;
-    return FLACB_OK;
+    st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = v;
+    st.out[st.pos++] = (int32_t)v;
+    if (--st.part_left == 0) st.state = st.parts_left > 0 ? ST_PART_HDR : ST_SUB_HDR + 100; /* 100+: subframe done */
 }
 
-/* One WARP per candidate, lane 0 does the work: Rice parsing is a serial, data dependent walk
- * through the bit stream, and 32 lanes walking 32 different frames diverge at every code (the
- * first version did that and ran 30x slower).  Parallelism comes from the frames: thousands of
- * independent warps, one per SM sub-partition slot. */
-constexpr int DECODE_WARPS = 4;
-
-__global__ void __launch_bounds__(32 * DECODE_WARPS) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand,
-                                                                         uint32_t n_cand, const u64 *tmp_off,
-                                                                         int32_t *tmp, int filter)
+__device__ void lane_step(LaneState &st, History &hist, int32_t *coef, int32_t *tmp, u64 tmp_off)
 {
-    const uint32_t ci = blockIdx.x * DECODE_WARPS + (threadIdx.x >> 5);
-    if (ci >= n_cand || (threadIdx.x & 31) != 0) return;
-    Candidate c = cand[ci];
-    c.tmp_off = tmp_off[ci];
-    if (filter && ci != 0 && c.status == FLACB_OK) {
-        /* cand[0] is only read here (its thread writes it back at the very end, same values
-         * for these fields) */
-        const int bs0 = cand[0].bs, nch0 = cand[0].nch, st0 = cand[0].status;
-        const u64 start0 = cand[0].start;
-        if (start0 == 0 && (st0 == FLACB_OK || st0 == STATUS_DEFERRED) && bs0 > 0 && (c.bs > bs0 || c.nch != nch0))
-            c.status = STATUS_DEFERRED;
+    BitReader &g = st.g;
+    switch (st.state) {
+    case ST_RICE: {
+        lane_refill(g);
+        if (g.buf == 0) { /* the unary run continues behind the buffered bits */
+            if (g.avail == 0 && g.next >= g.len) return lane_fail(st, FLACB_E_EOF);
+            st.cnt += (u64)g.avail;
+            g.avail = 0;
+            return;
+        }
+        const int z = __clzll(g.buf);
+        const u64 msb = st.cnt + (u64)z;
+        st.cnt = 0;
+        g.buf <<= z;
+        g.buf <<= 1;
+        g.avail -= z + 1;
+        lane_refill(g);
+        const u64 lsb = g.read(st.k);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        const u64 u = (msb << st.k) | lsb;
+        lane_store(st, hist, coef, (i64)(u >> 1) ^ -(i64)(u & 1)); /* utils.py:87-88 */
+        break;
     }
-    if (c.status == FLACB_OK) {
-        BitReader g;
-        g.init(s, len, c.start);
-        /* skip the header (already validated) */
-        uint32_t hb = c.hdr_bits;
-        while (hb >= 32) (void)g.read(32), hb -= 32;
-        (void)g.read((int)hb);
-        int rc = FLACB_OK;
-        for (int ch = 0; ch < c.nch && rc == FLACB_OK; ch++) {
-            /* the side channel carries one more bit (common.py:182-196) */
-            const int extra = (c.chcode == 8 && ch == 1) || (c.chcode == 9 && ch == 0) || (c.chcode == 10 && ch == 1);
-            rc = decode_subframe(g, c.bs, c.sample_size + extra, tmp + c.tmp_off + (u64)ch * (u64)c.bs);
-        }
-        if (rc == FLACB_OK) {
-            const int padn = (int)((8 - (g.bit_pos() & 7)) & 7); /* decoder.py:124-126 */
-            const uint32_t pad = g.read(padn);
-            if (g.eof) rc = FLACB_E_EOF;
-            else if (pad != 0) rc = FLACB_E_ASSERT;
-        }
-        if (rc == FLACB_OK) {
-            (void)g.read(16); /* CRC-16, never verified (decoder.py:128) */
-            if (g.eof) rc = FLACB_E_EOF;
-        }
-        c.status = rc;
-        c.end = rc == FLACB_OK ? g.bit_pos() >> 3 : 0;
+    case ST_ESCAPED: {
+        lane_refill(g);
+        const i64 r = g.read_signed(st.esc_size);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        lane_store(st, hist, coef, r);
+        break;
     }
-    cand[ci] = c;
+    case ST_PART_HDR: {
+        lane_refill(g);
+        const int first = st.parts_left == (1 << st.porder);
+        st.part_left = first ? (st.bs >> st.porder) - st.order : (st.bs >> st.porder);
+        st.parts_left--;
+        st.k = (int)g.read(st.method);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (st.k == (1 << st.method) - 1) { /* escaped partition */
+            st.esc_size = (int)g.read(5);
+            if (g.eof) return lane_fail(st, FLACB_E_EOF);
+            if (st.esc_size == 0 && st.part_left > 0) return lane_fail(st, FLACB_E_VALUE); /* sint(0) */
+            st.state = ST_ESCAPED;
+        } else st.state = ST_RICE;
+        if (st.part_left == 0) st.state = st.parts_left > 0 ? ST_PART_HDR : ST_SUB_HDR + 100;
+        break;
+    }
+    case ST_RES_HDR: {
+        lane_refill(g);
+        const uint32_t m = g.read(2);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (m > 1) return lane_fail(st, FLACB_E_VALUE); /* RiceCodingMethod(x) */
+        st.method = m == 0 ? 4 : 5;
+        st.porder = (int)g.read(4);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        const int nparts = 1 << st.porder;
+        if (st.bs % nparts != 0) return lane_fail(st, FLACB_E_ASSERT);
+        if (!((st.bs >> st.porder) > st.order)) return lane_fail(st, FLACB_E_ASSERT);
+        st.parts_left = nparts;
+        st.cnt = 0;
+        st.state = ST_PART_HDR;
+        break;
+    }
+    case ST_WARMUP: {
+        if (st.idx >= st.order) {
+            st.state = st.type >= 32 ? ST_LPC_HDR : ST_RES_HDR;
+            break;
+        }
+        if (st.ss <= 0 || st.ss > 40) return lane_fail(st, FLACB_E_VALUE);
+        if (st.idx >= st.bs) return lane_fail(st, FLACB_E_ASSERT); /* warm-up longer than the block */
+        lane_refill(g);
+        const i64 v = g.read_signed(st.ss);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        hist.push(v);
+        st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = v;
+        st.out[st.idx++] = (int32_t)v;
+        st.pos = st.idx;
+        break;
+    }
+    case ST_LPC_HDR: {
+        lane_refill(g);
+        st.precision = (int)g.read(4);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (st.precision == 15) return lane_fail(st, FLACB_E_ASSERT);
+        st.precision += 1;
+        st.shift = (int)g.read_signed(5);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        st.idx = 0;
+        st.state = ST_COEF;
+        break;
+    }
+    case ST_COEF: {
+        if (st.idx >= st.order) {
+            st.state = ST_RES_HDR;
+            break;
+        }
+        lane_refill(g);
+        coef[st.idx++] = (int32_t)g.read_signed(st.precision);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        break;
+    }
+    case ST_SUB_HDR: {
+        if (st.ch >= st.nch) {
+            st.state = ST_FRAME_END;
+            break;
+        }
+        lane_refill(g);
+        const uint32_t padbit = g.read(1);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (padbit != 0) return lane_fail(st, FLACB_E_ASSERT);
+        st.type = (int)g.read(6);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (!(st.type <= 1 || (st.type >= 8 && st.type <= 12) || st.type >= 32)) return lane_fail(st, FLACB_E_ASSERT);
+        const uint32_t wflag = g.read(1);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        /* the side channel carries one more bit (common.py:182-196) */
+        const int extra = (st.chcode == 8 && st.ch == 1) || (st.chcode == 9 && st.ch == 0) || (st.chcode == 10 && st.ch == 1);
+        st.ss = st.sample_size + extra;
+        st.out = tmp + tmp_off + (u64)st.ch * (u64)st.bs;
+        st.pos = 0, st.idx = 0, st.shift = 0, st.cnt = 0;
+        st.x1 = st.x2 = st.x3 = st.x4 = 0;
+        hist.head = 0;
+        st.order = st.type >= 32 ? (st.type & 31) + 1 : st.type >= 8 ? (st.type & 7) : 0;
+        st.state = wflag ? ST_WASTED : (st.type == 0 ? ST_CONST : st.type == 1 ? ST_VERBATIM : ST_WARMUP);
+        break;
+    }
+    case ST_WASTED: {
+        /* decoder.py:346-355: counts the zeros (one less than the format says) and never shifts the
+         * samples back; reproduced */
+        lane_refill(g);
+        if (g.buf == 0) {
+            if (g.avail == 0 && g.next >= g.len) return lane_fail(st, FLACB_E_EOF);
+            st.cnt += (u64)g.avail;
+            g.avail = 0;
+            return;
+        }
+        const int z = __clzll(g.buf);
+        const u64 wasted = st.cnt + (u64)z;
+        st.cnt = 0;
+        g.buf <<= z;
+        g.buf <<= 1;
+        g.avail -= z + 1;
+        st.ss -= (int)(wasted > 1000 ? 1000 : wasted);
+        st.state = st.type == 0 ? ST_CONST : st.type == 1 ? ST_VERBATIM : ST_WARMUP;
+        break;
+    }
+    case ST_CONST: {
+        if (st.ss <= 0 || st.ss > 40) return lane_fail(st, FLACB_E_VALUE);
+        lane_refill(g);
+        const i64 v = g.read_signed(st.ss);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        for (int i = 0; i < st.bs; i++) st.out[i] = (int32_t)v;
+        st.state = ST_SUB_HDR + 100;
+        break;
+    }
+    case ST_VERBATIM: {
+        if (st.ss <= 0 || st.ss > 40) return lane_fail(st, FLACB_E_VALUE);
+        if (st.pos >= st.bs) {
+            st.state = ST_SUB_HDR + 100;
+            break;
+        }
+        lane_refill(g);
+        st.out[st.pos++] = (int32_t)g.read_signed(st.ss);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        break;
+    }
+    case ST_FRAME_END: {
+        const int padn = (int)((8 - (g.bit_pos() & 7)) & 7); /* decoder.py:124-126 */
+        lane_refill(g);
+        const uint32_t pad = g.read(padn);
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        if (pad != 0) return lane_fail(st, FLACB_E_ASSERT);
+        lane_refill(g);
+        (void)g.read(16); /* CRC-16, never verified (decoder.py:128) */
+        if (g.eof) return lane_fail(st, FLACB_E_EOF);
+        st.status = FLACB_OK;
+        st.state = ST_DONE;
+        break;
+    }
+    default:
+        break;
+    }
+    if (st.state == ST_SUB_HDR + 100) { /* subframe complete */
+        if (st.type >= 32 && st.shift < 0) return lane_fail(st, FLACB_E_VALUE); /* >> negative, decoder.py:497 */
+        st.ch++;
+        st.state = ST_SUB_HDR;
+    }
+}
+
+__global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
+                                                           const u64 *tmp_off, int32_t *tmp, int filter)
+{
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    LaneState st;
+    History hist;
+    int32_t coef[FLACB_MAX_LPC];
+    hist.head = 0;
+    st.state = ST_DONE;
+    st.status = FLACB_E_EOF;
+    Candidate c;
+    u64 my_off = 0;
+    if (ci < n_cand) {
+        c = cand[ci];
+        my_off = tmp_off[ci];
+        c.tmp_off = my_off;
+        if (filter && ci != 0 && c.status == FLACB_OK) {
+            /* cand[0] is only read here (its lane writes it back at the very end, same values
+             * for these fields) */
+            const int bs0 = cand[0].bs, nch0 = cand[0].nch, st0 = cand[0].status;
+            const u64 start0 = cand[0].start;
+            if (start0 == 0 && (st0 == FLACB_OK || st0 == STATUS_DEFERRED) && bs0 > 0 && (c.bs > bs0 || c.nch != nch0))
+                c.status = STATUS_DEFERRED;
+        }
+        if (c.status == FLACB_OK) {
+            st.g.init(s, len, c.start + c.hdr_bits / 8); /* the header is byte aligned and already parsed */
+            st.state = ST_SUB_HDR;
+            st.ch = 0, st.nch = c.nch, st.chcode = c.chcode, st.bs = c.bs, st.sample_size = c.sample_size;
+            st.type = 0, st.order = 0, st.shift = 0, st.cnt = 0;
+        }
+    }
+    const bool active = ci < n_cand && c.status == FLACB_OK;
+    while (__any_sync(0xffffffffu, st.state != ST_DONE)) {
+        if (st.state != ST_DONE) lane_step(st, hist, coef, tmp, my_off);
+    }
+    if (ci < n_cand) {
+        if (active) {
+            c.status = st.status;
+            c.end = st.status == FLACB_OK ? st.g.bit_pos() >> 3 : 0;
+        }
+        cand[ci] = c;
+    }
 }
 
 /* ---- D4 ------------------------------------------------------------------------------ */

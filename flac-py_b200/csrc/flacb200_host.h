@@ -143,9 +143,19 @@ struct LaunchShape {
 
 template <class LayoutFn>
 inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t smem_optin, size_t smem_per_sm,
-                              LayoutFn layout_total)
+                              LayoutFn layout_total, int lpc = 0)
 {
     LaunchShape best = {0, 0, 0, 0};
+    if (lpc) {
+        /* measured (profiles/): with the LPC analysis in the kernel, two resident frames at 96
+         * registers and every plane in shared memory beat three at 72 registers */
+        const int threads = pick_threads(block_size, e, 288);
+        const size_t dyn = layout_total(threads, 1);
+        if (dyn + static_smem <= smem_optin && 2 * (dyn + static_smem + 1024) <= smem_per_sm && 2 * 96 * threads <= 65536) {
+            best = {threads, 1, 2, 0};
+            return best;
+        }
+    }
     for (int variant = 1; variant >= 0; variant--) {
         const int maxb = variant ? 288 : 576;
         const int regs = variant ? 72 : 96;

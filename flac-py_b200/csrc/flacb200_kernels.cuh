@@ -98,6 +98,9 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     if (words < frame_words) words = frame_words;
     if (words < 512) words = 512;
     if (words > (uint32_t)STG_WORDS) words = (uint32_t)STG_WORDS;
+    /* the window doubles as scratch for the autocorrelation partials: 24 bytes per warp and lag */
+    const uint32_t autoc_words = (uint32_t)((threads + 31) / 32) * (FLACB_MAX_LPC + 1) * 6 + 8;
+    if (L > 0 && words < autoc_words) words = autoc_words;
     l.stg_words = words;
     l.xs_all = all_planes;
     uint32_t off = 0;
@@ -164,7 +167,7 @@ struct Decision {
 
 struct Shared {
     double autoc[FLACB_MAX_LPC + 1];
-    i64 isum[FLACB_MAX_LPC + 1]; /* exact integer part of the autocorrelation */
+    double lev_prod[FLACB_MAX_LPC]; /* coefs[j] * autoc[k+1-j] of the current Levinson step */
     int32_t qshift[FLACB_MAX_LPC], qncoef[FLACB_MAX_LPC], qstat[FLACB_MAX_LPC];
     uint32_t qabs[FLACB_MAX_LPC];
     u64 lpc_err[FLACB_MAX_LPC];
@@ -206,6 +209,7 @@ struct Blk {
     int32_t *qc;   /* [L][L] quantised coefficients per order */
     int ldL;       /* row stride of ldc / qc */
     uint32_t stg_words;
+    uint32_t wx_bytes; /* bytes of the residual + running-sum area (scratch of the autocorrelation) */
     const double *win;
     int flat_lo, flat_hi;
     __device__ Blk(const EncParams &p_, Shared &sh_) : p(p_), sh(sh_) {}
@@ -460,6 +464,10 @@ template <int LG, int LGI>
 __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
 {
     const int n = b.n;
+    /* per-warp partial results live in the (idle) staging window of the packer:
+     * [warp][lag] exact integer part, then [warp][lag] double-double part.  One barrier for all. */
+    i64 *part_i = (i64 *)b.stg;
+    double2 *part_d = (double2 *)(part_i + ((b.nwarps * (FLACB_MAX_LPC + 1) + 1) & ~1)); /* 16-byte aligned */
     /* ---- integer part ---- */
     for (int lag0 = 0; lag0 <= L; lag0 += LGI) {
         i64 acc[LGI];
@@ -489,19 +497,30 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
         for (int l = 0; l < LGI; l++) {
             if (lag0 + l <= L) {
                 const i64 t = warp_any ? warp_sum_i64(acc[l]) : 0;
-                if (b.lane == 0) b.red[b.warp * RED_STRIDE + lag0 + l] = (u64)t; /* one writer per slot */
+                if (b.lane == 0) part_i[b.warp * (FLACB_MAX_LPC + 1) + lag0 + l] = t; /* one writer per slot */
             }
         }
     }
-    __syncthreads();
-    if (b.tid <= L) {
-        u64 t = 0;
-        for (int w = 0; w < b.nwarps; w++) t += b.red[w * RED_STRIDE + b.tid];
-        b.sh.isum[b.tid] = (i64)t;
-    }
-    __syncthreads();
     /* ---- windowed part, double-double ---- */
-    double2 *redd = (double2 *)b.red;
+    /* Windowed samples w = fl(x * win) of the two tapered ends, computed once and kept as doubles
+     * in the (still unused) residual + running-sum area: index i -> i + i/8 keeps the stride-8
+     * reads of a half-warp on distinct 8-byte banks.  Front range [0, A), back range [Bq, n+pad). */
+    double *wxs = (double *)b.res;
+    int A = b.flat_lo + 2 * E + L;
+    int Bq = b.flat_hi - L - 2 * E;
+    if (Bq > n - L - 2 * E - 2) Bq = n - L - 2 * E - 2;
+    Bq = Bq < 0 ? 0 : (Bq / E) * E;
+    const int top = n + E + L + 8; /* exclusive; window and samples are zero padded behind n */
+    if (A >= Bq) A = top, Bq = top; /* no flat middle: one range */
+    const int count = A + (top - Bq);
+    const bool stored = (size_t)(count + (count >> 3) + 2) * 8 <= b.wx_bytes;
+    if (stored) {
+        for (int t = b.tid; t < count; t += b.B) {
+            const int i = t < A ? t : Bq + (t - A);
+            wxs[t + (t >> 3)] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i))], b.win[i]);
+        }
+        __syncthreads();
+    }
     for (int lag0 = 0; lag0 <= L; lag0 += LG) {
         double s[LG], c[LG];
 #pragma unroll
@@ -510,13 +529,21 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
             const int i0 = (tile * b.B + b.tid) * E;
             if (i0 < n && !autoc_flat(b, i0, L)) {
                 double wa[E], wb[E + LG - 1];
+                if (stored) {
+                    const int t0 = i0 < A ? i0 : A + (i0 - Bq); /* a thread's reads stay inside one range */
 #pragma unroll
-                for (int e = 0; e < E; e++)
-                    wa[e] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
+                    for (int e = 0; e < E; e++) wa[e] = wxs[(t0 + e) + ((t0 + e) >> 3)];
 #pragma unroll
-                for (int j = 0; j < E + LG - 1; j++) {
-                    const int idx = i0 + lag0 + j;
-                    wb[j] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + idx))], b.win[idx]);
+                    for (int j = 0; j < E + LG - 1; j++) wb[j] = wxs[(t0 + lag0 + j) + ((t0 + lag0 + j) >> 3)];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        wa[e] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
+#pragma unroll
+                    for (int j = 0; j < E + LG - 1; j++) {
+                        const int idx = i0 + lag0 + j;
+                        wb[j] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + idx))], b.win[idx]);
+                    }
                 }
 #pragma unroll
                 for (int l = 0; l < LG; l++) {
@@ -533,43 +560,41 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
         }
 #pragma unroll
         for (int l = 0; l < LG; l++) {
+            if (lag0 + l <= L) {
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double s2 = __shfl_xor_sync(FULL, s[l], off);
-                const double c2 = __shfl_xor_sync(FULL, c[l], off);
-                dd_add(s[l], c[l], s2);
-                c[l] = __dadd_rn(c[l], c2);
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double s2 = __shfl_xor_sync(FULL, s[l], off);
+                    const double c2 = __shfl_xor_sync(FULL, c[l], off);
+                    dd_add(s[l], c[l], s2);
+                    c[l] = __dadd_rn(c[l], c2);
+                }
+                if (b.lane == 0) part_d[b.warp * (FLACB_MAX_LPC + 1) + lag0 + l] = make_double2(s[l], c[l]);
             }
         }
-        if (b.lane == 0) {
-#pragma unroll
-            for (int l = 0; l < LG; l++) redd[b.warp * LG + l] = make_double2(s[l], c[l]);
-        }
-        __syncthreads();
-        for (int l = b.warp; l < LG && lag0 + l <= L; l += b.nwarps) { /* a warp per lag combines the warps' sums */
-            double S = 0.0, C = 0.0;
-            if (b.lane < b.nwarps) {
-                const double2 v = redd[b.lane * LG + l];
-                S = v.x, C = v.y;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double s2 = __shfl_xor_sync(FULL, S, off);
-                const double c2 = __shfl_xor_sync(FULL, C, off);
-                dd_add(S, C, s2);
-                C = __dadd_rn(C, c2);
-            }
-            if (b.lane == 0) {
-                /* the exact integer part, split into two doubles that each hold it exactly */
-                const i64 iv = b.sh.isum[lag0 + l];
-                const i64 hi = iv & ~(i64)0x7FF, lo = iv & (i64)0x7FF;
-                dd_add(S, C, (double)hi);
-                dd_add(S, C, (double)lo);
-                b.sh.autoc[lag0 + l] = __dadd_rn(S, C);
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    /* ---- a warp per lag combines the warps' partial sums; rounded once at the end ---- */
+    for (int lag = b.warp; lag <= L; lag += b.nwarps) {
+        double S = 0.0, C = 0.0;
+        if (b.lane < b.nwarps) {
+            const double2 v = part_d[b.lane * (FLACB_MAX_LPC + 1) + lag];
+            S = v.x, C = v.y;
+            /* the exact integer part, split into two doubles that each hold it exactly */
+            const i64 iv = part_i[b.lane * (FLACB_MAX_LPC + 1) + lag];
+            const i64 hi = iv & ~(i64)0x7FF, lo = iv & (i64)0x7FF;
+            dd_add(S, C, (double)hi);
+            dd_add(S, C, (double)lo);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double s2 = __shfl_xor_sync(FULL, S, off);
+            const double c2 = __shfl_xor_sync(FULL, C, off);
+            dd_add(S, C, s2);
+            C = __dadd_rn(C, c2);
+        }
+        if (b.lane == 0) b.sh.autoc[lag] = __dadd_rn(S, C);
+    }
+    __syncthreads();
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -591,10 +616,12 @@ __device__ void levinson(Blk &b, int L)
     int stat = 0;
 #pragma unroll 1
     for (int k = 0; k < L; k++) {
-        const double prod = (lane <= k) ? __dmul_rn(cj, sh.autoc[k + 1 - lane]) : 0.0;
+        if (lane <= k) sh.lev_prod[lane] = __dmul_rn(cj, sh.autoc[k + 1 - lane]);
+        __syncwarp();
         double lambda = 0.0;
-#pragma unroll 1
-        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, __shfl_sync(FULL, prod, j)); /* encoder.py:467 */
+#pragma unroll 4
+        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, sh.lev_prod[j]); /* encoder.py:467 */
+        __syncwarp();
         if (error == 0.0) { stat = FLACB_E_ZERODIV; break; }                                /* encoder.py:469 */
         lambda = __ddiv_rn(lambda, error);
         /* encoder.py:471-474: coefs[i] <- coefs[i] + lambda * coefs[k+1-i] for i in 0..k+1 */
@@ -1445,6 +1472,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.qc = (int32_t *)(smem + lay.qc);
     b.ldL = p.L;
     b.stg_words = lay.stg_words;
+    b.wx_bytes = lay.kall - lay.res;
 
     /* ---- phase 0 + 1 ---- */
     if (lay.xs_all) load_planes(b, -1);

@@ -181,6 +181,8 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
     return sim::exchange(v, lane >= (int)d ? lane - (int)d : lane);
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return sim::exchange(v, src & 31); }
+static inline unsigned __ballot_sync(unsigned, int pred);
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
     sim::State &s = sim::st();

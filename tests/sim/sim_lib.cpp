@@ -69,7 +69,7 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     auto layout_total = [&](int threads, int all_planes) {
         return (size_t)make_layout(block_size, channels, bits, rice_max, max_lpc_order, threads, all_planes).total;
     };
-    LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total);
+    LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total, max_lpc_order > 0);
     if (shape.threads == 0) return FLACB_E_UNSUPPORTED;
     if (smem_limit == 1) shape.all_planes = 0;
     if (smem_limit == 2) shape.all_planes = 1;
@@ -180,9 +180,9 @@ static int sim_decode_impl(const uint8_t *frames, uint64_t len, int streaminfo_b
         sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data(), check_crc8); });
     sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
     std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
-    const unsigned nbd = (unsigned)((n_cand + DECODE_WARPS - 1) / DECODE_WARPS);
+    const unsigned nbd = (unsigned)((n_cand + 31) / 32);
     for (unsigned b = 0; b < nbd; b++)
-        sim::run_block(b, nbd, 32 * DECODE_WARPS, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8); });
+        sim::run_block(b, nbd, 32, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8); });
     DecodeResult res;
     sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
     if (res.status == STATUS_CRC8_MISMATCH || res.status == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH;
