@@ -150,16 +150,18 @@ inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t 
         /* measured (profiles/): with the LPC analysis in the kernel, two resident frames at 96
          * registers and every plane in shared memory beat three at 72 registers */
         const int threads = pick_threads(block_size, e, 288);
-        const size_t dyn = layout_total(threads, 1);
-        if (dyn + static_smem <= smem_optin && 2 * (dyn + static_smem + 1024) <= smem_per_sm && 2 * 96 * threads <= 65536) {
-            best = {threads, 1, 2, 0};
-            return best;
+        for (int mode = 2; mode >= 1; mode--) { /* 2: also keep every channel's residual for phase 3 */
+            const size_t dyn = layout_total(threads, mode);
+            if (dyn + static_smem <= smem_optin && 2 * (dyn + static_smem + 1024) <= smem_per_sm && 2 * 96 * threads <= 65536) {
+                best = {threads, mode, 2, 0};
+                return best;
+            }
         }
     }
     for (int variant = 1; variant >= 0; variant--) {
         const int maxb = variant ? 288 : 576;
         const int regs = variant ? 72 : 96;
-        for (int all_planes = 1; all_planes >= 0; all_planes--) {
+        for (int all_planes = 2; all_planes >= 0; all_planes--) {
             const int threads = pick_threads(block_size, e, maxb);
             const size_t dyn = layout_total(threads, all_planes);
             if (dyn + static_smem > smem_optin) continue;

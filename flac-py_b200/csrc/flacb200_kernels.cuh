@@ -75,7 +75,8 @@ __host__ __device__ __forceinline__ uint32_t padidx(uint32_t i) { return i + (i 
 
 struct SmemLayout {
     uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, ldc, qc, total;
-    int xs_all;
+    uint32_t chan_stride; /* bytes between the residual / running-sum / parameter areas of two channels */
+    int xs_all, res_all;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -102,12 +103,21 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     const uint32_t autoc_words = (uint32_t)((threads + 31) / 32) * (FLACB_MAX_LPC + 1) * 6 + 8;
     if (L > 0 && words < autoc_words) words = autoc_words;
     l.stg_words = words;
-    l.xs_all = all_planes;
+    /* all_planes: 0 one plane (reloaded per channel), 1 every plane resident, 2 every plane and
+     * every channel's residual / running sums / Rice parameters resident (phase 3 recomputes
+     * nothing) */
+    l.xs_all = all_planes >= 1;
+    l.res_all = all_planes >= 2;
     uint32_t off = 0;
-    l.xs = off; off += all_planes ? plane * (uint32_t)channels : plane;
-    l.res = off; off += align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
-    l.cum = off; off += align16(((uint32_t)nmax / E + 4) * 8);
-    l.kall = off; off += align16(2u << rmax);
+    l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
+    const uint32_t res_b = align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
+    const uint32_t cum_b = align16(((uint32_t)nmax / E + 4) * 8);
+    const uint32_t kall_b = align16(2u << rmax);
+    l.chan_stride = res_b + cum_b + kall_b;
+    l.res = off;
+    l.cum = off + res_b;
+    l.kall = off + res_b + cum_b;
+    off += l.chan_stride * (l.res_all ? (uint32_t)channels : 1u);
     l.stg = off; off += align16((words + 4) * 4);
     /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
     uint32_t red_b = align16((MAXB / 32) * RED_STRIDE * 8);
@@ -184,6 +194,11 @@ struct Shared {
     u64 frame_off;
     uint32_t frame_bytes, payload_bytes;
     int status, writable, range_flag, have_off;
+    /* where the frame goes (copied from the launch parameters for the out-of-line helpers) */
+    uint8_t *o_out;
+    u64 o_cap, o_slot_stride;
+    u64 *o_lb_state, *o_frame_off;
+    uint32_t o_n_frames;
     uint32_t frame;
     uint32_t scan_warp[33];
     u64 scan_warp64[33];
@@ -339,11 +354,13 @@ __device__ __forceinline__ int32_t load_sample(const uint8_t *base, u64 s, int c
     return v;
 }
 
-/* c < 0: all channels into their planes (xs_all); otherwise channel c into plane 0 */
-__device__ void load_planes(Blk &b, int c_only)
+/* c_only < 0: all channels into their planes (xs_all); otherwise channel c_only into plane 0.
+ * CH: compile-time channel count for the common layouts (0 = any, divides at run time). */
+template <int CH>
+__device__ void load_planes_t(Blk &b, int c_only)
 {
     const EncParams &p = b.p;
-    const int ch = p.channels;
+    const int ch = CH ? CH : p.channels;
     const uint8_t *base = p.pcm + (u64)b.sh.frame * (u64)p.block_size * (u64)ch * (u64)p.cbytes;
     const bool aligned = (((uintptr_t)base) & (uintptr_t)(p.cbytes - 1)) == 0 || p.cbytes == 3 ||
                          p.cbytes == 1;
@@ -359,12 +376,7 @@ __device__ void load_planes(Blk &b, int c_only)
     int done = 0; /* samples [0, done) are handled by a vector path, the rest one by one */
     auto put = [&](int sidx, int32_t v) {
         /* sample `sidx` of the interleaved frame -> its plane */
-        int i, c;
-        if (ch == 1) i = sidx, c = 0;
-        else if (ch == 2) i = sidx >> 1, c = sidx & 1;
-        else if (ch == 4) i = sidx >> 2, c = sidx & 3;
-        else if (ch == 8) i = sidx >> 3, c = sidx & 7;
-        else i = sidx / ch, c = sidx - i * ch;
+        const int i = sidx / ch, c = sidx - i * ch; /* shifts for the compile-time counts */
         if (c_only < 0) b.xs[(uint32_t)c * b.xwords + padidx((uint32_t)(GUARD + i))] = v;
         else if (c == c_only) b.xs[padidx((uint32_t)(GUARD + i))] = v;
     };
@@ -397,6 +409,16 @@ __device__ void load_planes(Blk &b, int c_only)
     }
     for (int sidx = done + b.tid; sidx < total; sidx += b.B) put(sidx, load_sample(base, (u64)sidx, p.cbytes, p.bps, aligned));
     __syncthreads();
+}
+
+__device__ __forceinline__ void load_planes(Blk &b, int c_only)
+{
+    switch (b.p.channels) {
+    case 1: load_planes_t<1>(b, c_only); break;
+    case 2: load_planes_t<2>(b, c_only); break;
+    case 8: load_planes_t<8>(b, c_only); break;
+    default: load_planes_t<0>(b, c_only); break;
+    }
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -1015,14 +1037,18 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t bb)
 /* phase 2, deferred: byte offset of this frame = sum of the sizes of all frames in front of it.
  * Decoupled look-back, one warp, 32 predecessors per probe: sizes are summed backwards until a
  * frame that already knows its own inclusive prefix is met. */
-__device__ FLACB_OUTLINE void resolve_offset(Blk &b)
+__device__ __noinline__ void resolve_offset(Shared *shp, int tid)
 {
-    Shared &sh = b.sh;
-    const EncParams &p = b.p;
+    /* out of line and on plain arguments: called from every flush site, and a reference to the
+     * per-thread block state would force that state into local memory */
+    Shared &sh = *shp;
+    const int lane = tid & 31, warp = tid >> 5;
     const uint32_t f = sh.frame;
-    if (p.slot_stride) {
-        if (b.tid == 0) sh.frame_off = (u64)f * p.slot_stride;
-    } else if (b.warp == 0) {
+    const u64 slot_stride = sh.o_slot_stride;
+    u64 *lb_state = sh.o_lb_state;
+    if (slot_stride) {
+        if (tid == 0) sh.frame_off = (u64)f * slot_stride;
+    } else if (warp == 0) {
         const u64 mine = (u64)sh.frame_bytes;
         u64 excl = 0;
         bool failed = false;
@@ -1030,9 +1056,9 @@ __device__ FLACB_OUTLINE void resolve_offset(Blk &b)
             int64_t j = (int64_t)f - 1;
             uint32_t spins = 0;
             while (true) {
-                const int64_t idx = j - b.lane;
+                const int64_t idx = j - lane;
                 u64 s = LB_PREFIX; /* before frame 0: an empty prefix */
-                if (idx >= 0) s = *(volatile u64 *)&p.lb_state[idx];
+                if (idx >= 0) s = *(volatile u64 *)&lb_state[idx];
                 const uint32_t flag = (uint32_t)(s >> 62);
                 const unsigned has_prefix = __ballot_sync(FULL, flag == 2);
                 const unsigned invalid = __ballot_sync(FULL, flag == 0);
@@ -1043,26 +1069,27 @@ __device__ FLACB_OUTLINE void resolve_offset(Blk &b)
                     __nanosleep(64);
                     continue;
                 }
-                u64 v = (b.lane <= first_prefix) ? (s & LB_VALUE) : 0ull;
+                u64 v = (lane <= first_prefix) ? (s & LB_VALUE) : 0ull;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
                 excl += v;
                 if (first_prefix < 32) break;
                 j -= 32;
             }
-            if (b.lane == 0) atomicExch(&p.lb_state[f], LB_PREFIX | ((excl + mine) & LB_VALUE));
+            if (lane == 0) atomicExch(&lb_state[f], LB_PREFIX | ((excl + mine) & LB_VALUE));
         }
-        if (b.lane == 0) {
+        if (lane == 0) {
             sh.frame_off = excl;
-            p.frame_off[f] = excl;
-            if (f == p.n_frames - 1) p.frame_off[p.n_frames] = excl + mine;
-            if (failed) set_status(b, FLACB_E_INTERNAL);
+            sh.o_frame_off[f] = excl;
+            if (f == sh.o_n_frames - 1) sh.o_frame_off[sh.o_n_frames] = excl + mine;
+            if (failed && sh.status == 0) sh.status = FLACB_E_INTERNAL;
         }
     }
     __syncthreads();
-    if (b.tid == 0) {
-        const u64 lim = p.slot_stride ? p.slot_stride : p.out_cap - (sh.frame_off < p.out_cap ? sh.frame_off : p.out_cap);
-        sh.writable = (u64)sh.frame_bytes <= lim && (p.slot_stride == 0 || sh.frame_off + sh.frame_bytes <= p.out_cap) &&
+    if (tid == 0) {
+        const u64 out_cap = sh.o_cap;
+        const u64 lim = slot_stride ? slot_stride : out_cap - (sh.frame_off < out_cap ? sh.frame_off : out_cap);
+        sh.writable = (u64)sh.frame_bytes <= lim && (slot_stride == 0 || sh.frame_off + sh.frame_bytes <= out_cap) &&
                       sh.status != FLACB_E_INTERNAL;
         if (!sh.writable && sh.status == 0) sh.status = FLACB_E_NOSPACE;
         sh.have_off = 1;
@@ -1075,38 +1102,39 @@ __device__ FLACB_OUTLINE void resolve_offset(Blk &b)
  * zero init and no final xor, crc(A || B) = crc(A) * x^(8|B|) + crc(B), so a slice's CRC times
  * x^(8 * bytes behind it) can simply be xor-ed into the frame's.  Then the window is rebased at
  * word `wend` (the partial word, if any, moves to the front). */
-__device__ FLACB_OUTLINE void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
+__device__ __noinline__ void flush_window_impl(Shared *shp, uint32_t *stg, uint32_t stg_words, int tid, int B,
+                                              uint32_t nbytes, uint32_t wend)
 {
-    Shared &sh = b.sh;
-    if (!sh.have_off) resolve_offset(b); /* block-uniform */
+    Shared &sh = *shp;
+    if (!sh.have_off) resolve_offset(shp, tid); /* block-uniform */
     const uint32_t byte0 = sh.wbase * 4u; /* frame-relative */
     if (sh.writable && nbytes) {
         /* staging words hold the stream MSB first; memory wants those bytes in order.  Aligned
          * 32-bit stores for the body, single bytes in front of / behind it. */
-        uint8_t *dst = b.p.out + sh.frame_off + byte0;
+        uint8_t *dst = sh.o_out + sh.frame_off + byte0;
         uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
         if (head > nbytes) head = nbytes;
         const uint32_t nq = (nbytes - head) >> 2;
         const uint32_t tail0 = head + nq * 4u;
-        for (uint32_t idx = (uint32_t)b.tid; idx < head + (nbytes - tail0); idx += (uint32_t)b.B) {
+        for (uint32_t idx = (uint32_t)tid; idx < head + (nbytes - tail0); idx += (uint32_t)B) {
             const uint32_t i = idx < head ? idx : tail0 + (idx - head);
-            dst[i] = (uint8_t)(b.stg[i >> 2] >> (24u - 8u * (i & 3u)));
+            dst[i] = (uint8_t)(stg[i >> 2] >> (24u - 8u * (i & 3u)));
         }
         uint32_t *dstw = (uint32_t *)(dst + head);
         const uint32_t r = head & 3u; /* byte offset of every aligned word inside the staging words */
-        for (uint32_t q = (uint32_t)b.tid; q < nq; q += (uint32_t)b.B) {
+        for (uint32_t q = (uint32_t)tid; q < nq; q += (uint32_t)B) {
             const uint32_t j = (head + 4u * q) >> 2;
-            const uint32_t s0 = __byte_perm(b.stg[j], 0, 0x0123), s1 = __byte_perm(b.stg[j + 1], 0, 0x0123);
+            const uint32_t s0 = __byte_perm(stg[j], 0, 0x0123), s1 = __byte_perm(stg[j + 1], 0, 0x0123);
             dstw[q] = r == 0 ? s0 : __funnelshift_r(s0, s1, 8u * r);
         }
     }
     const uint32_t nslices = (nbytes + CRC_SLICE - 1) / CRC_SLICE;
-    for (uint32_t sl = (uint32_t)b.tid; sl < nslices; sl += (uint32_t)b.B) {
+    for (uint32_t sl = (uint32_t)tid; sl < nslices; sl += (uint32_t)B) {
         const uint32_t lo = sl * CRC_SLICE;
         const uint32_t hi = lo + CRC_SLICE < nbytes ? lo + CRC_SLICE : nbytes;
         uint32_t c = 0;
         for (uint32_t idx = lo; idx < hi; idx++) {
-            const uint32_t byte = (b.stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
+            const uint32_t byte = (stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
             c = ((c << 8) ^ sh.crc16_tab[(c >> 8) ^ byte]) & 0xFFFFu;
         }
         const uint32_t behind = sh.payload_bytes - (byte0 + hi);
@@ -1114,16 +1142,21 @@ __device__ FLACB_OUTLINE void flush_window(Blk &b, uint32_t nbytes, uint32_t wen
         atomicXor(&sh.crc, gf16_mul(c, w));
     }
     const uint32_t carry_idx = wend - sh.wbase;
-    const uint32_t carry = carry_idx <= b.stg_words ? b.stg[carry_idx] : 0u;
+    const uint32_t carry = carry_idx <= stg_words ? stg[carry_idx] : 0u;
     /* nothing beyond the word the bit cursor is in has been written */
     uint32_t used = (sh.pos >> 5) - sh.wbase;
     if (used < (nbytes + 3u) / 4u) used = (nbytes + 3u) / 4u; /* a tile wider than the window is flushed mid-way */
     used += 2u;
-    if (used > b.stg_words + 4u) used = b.stg_words + 4u;
+    if (used > stg_words + 4u) used = stg_words + 4u;
     __syncthreads();
-    for (uint32_t idx = (uint32_t)b.tid; idx < used; idx += (uint32_t)b.B) b.stg[idx] = idx == 0 ? carry : 0u;
-    if (b.tid == 0) sh.wbase = wend;
+    for (uint32_t idx = (uint32_t)tid; idx < used; idx += (uint32_t)B) stg[idx] = idx == 0 ? carry : 0u;
+    if (tid == 0) sh.wbase = wend;
     __syncthreads();
+}
+
+__device__ __forceinline__ void flush_window(Blk &b, uint32_t nbytes, uint32_t wend)
+{
+    flush_window_impl(&b.sh, b.stg, b.stg_words, b.tid, b.B, nbytes, wend);
 }
 
 /* thread-local concatenation of this thread's fields; see pack_residual */
@@ -1444,6 +1477,8 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         sh.frame = p.slot_stride ? blockIdx.x : atomicAdd(p.ticket, 1u);
         sh.status = 0;
         sh.range_flag = 0;
+        sh.o_out = p.out, sh.o_cap = p.out_cap, sh.o_slot_stride = p.slot_stride;
+        sh.o_lb_state = p.lb_state, sh.o_frame_off = p.frame_off, sh.o_n_frames = p.n_frames;
         sh.crc = 0;
         sh.pos = 0;
         sh.wbase = 0;
@@ -1461,9 +1496,13 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     const SmemLayout &lay = p.lay;
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
-    b.res = (uint32_t *)(smem + lay.res);
-    b.cum = (u64 *)(smem + lay.cum);
-    b.kall = (uint8_t *)(smem + lay.kall);
+    auto select_channel = [&](int c) { /* residual, running sums, Rice parameters of channel c */
+        const uint32_t o = lay.res_all ? (uint32_t)c * lay.chan_stride : 0u;
+        b.res = (uint32_t *)(smem + lay.res + o);
+        b.cum = (u64 *)(smem + lay.cum + o);
+        b.kall = (uint8_t *)(smem + lay.kall + o);
+    };
+    select_channel(0);
     b.stg = (uint32_t *)(smem + lay.stg);
     b.fb = (uint32_t *)(smem + lay.fb);
     b.pst = (uint32_t *)(smem + lay.pst);
@@ -1478,6 +1517,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     if (lay.xs_all) load_planes(b, -1);
     for (int c = 0; c < p.channels; c++) {
         if (!lay.xs_all) load_planes(b, c);
+        select_channel(c);
         analyse_channel<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
     }
 
@@ -1510,9 +1550,11 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     for (int c = 0; c < p.channels; c++) {
         const Decision &d = sh.dec[c];
         const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
-        if (!lay.xs_all) load_planes(b, c);
-        residual_and_cum<LMAX>(b, x, d);
-        { /* Rice parameters of the chosen order */
+        select_channel(c);
+        if (!lay.res_all) {
+            /* only one channel's residual fits: recompute it and the chosen order's parameters */
+            if (!lay.xs_all) load_planes(b, c);
+            residual_and_cum<LMAX>(b, x, d);
             const int psz = b.n >> d.porder;
             for (int pi = b.tid; pi < (1 << d.porder); pi += b.B) {
                 const int start = pi * psz < d.warm ? d.warm : pi * psz;
