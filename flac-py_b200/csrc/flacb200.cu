@@ -333,8 +333,8 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     if ((rc = sl.frame_off.ensure((n_frames + 1) * 8))) return rc;
     if ((rc = sl.status.ensure(n_frames * 4))) return rc;
     if ((rc = sl.lb.ensure(n_frames * 8))) return rc;
-    if ((rc = sl.misc.ensure(128))) return rc;
-    if ((rc = sl.h_meta.ensure((n_frames + 1) * 8 + n_frames * 4 + 64 + 16))) return rc;
+    if ((rc = sl.misc.ensure(512))) return rc;
+    if ((rc = sl.h_meta.ensure((n_frames + 1) * 8 + n_frames * 4 + 256 + 16))) return rc;
 
     EncParams p;
     memset(&p, 0, sizeof(p));
@@ -380,7 +380,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         p.out_cap = out_cap;
     }
 
-    CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 128, sl.stream));
+    CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 512, sl.stream));
     CUDA_TRY(cudaMemsetAsync(sl.lb.p, 0, n_frames * 8, sl.stream));
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
 #define FLACB_LAUNCH(LM, TB, MB)                                                                                   \
@@ -409,11 +409,11 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     uint8_t *h = (uint8_t *)sl.h_meta.p;
     meta.h_frame_off = (u64 *)h;
     meta.h_stats = (u64 *)(h + (n_frames + 1) * 8);
-    meta.h_status = (int32_t *)(h + (n_frames + 1) * 8 + 64);
+    meta.h_status = (int32_t *)(h + (n_frames + 1) * 8 + 256);
     meta.threads = B;
     meta.smem = (int)lay.total;
     CUDA_TRY(cudaMemcpyAsync(meta.h_frame_off, sl.frame_off.p, (n_frames + 1) * 8, cudaMemcpyDeviceToHost, sl.stream));
-    CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 64, cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 256, cudaMemcpyDeviceToHost, sl.stream));
     CUDA_TRY(cudaMemcpyAsync(meta.h_status, sl.status.p, n_frames * 4, cudaMemcpyDeviceToHost, sl.stream));
     return FLACB_OK;
 }
@@ -520,6 +520,15 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         if (frame_offsets)
             for (u64 f = 0; f <= pd.nfr; f++) frame_offsets[pd.f0 + f] = host_off + pd.meta.h_frame_off[f];
         for (int o = 0; o < 6; o++) hist[o] += pd.meta.h_stats[o];
+#ifdef FLACB_PHASE_TIMING
+        {
+            u64 tot = 0;
+            for (int k = 0; k < 12; k++) tot += pd.meta.h_stats[8 + k];
+            fprintf(stderr, "phase cycles %%:");
+            for (int k = 0; k < 12; k++) fprintf(stderr, " %d:%.1f", k, 100.0 * (double)pd.meta.h_stats[8 + k] / (double)(tot ? tot : 1));
+            fprintf(stderr, "  (avg cycles/frame %.0f)\n", (double)tot / (double)pd.nfr);
+        }
+#endif
         ood += pd.meta.h_stats[6];
         threads = pd.meta.threads, smem = pd.meta.smem;
         if (host_out) {

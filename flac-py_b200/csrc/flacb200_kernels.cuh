@@ -60,6 +60,21 @@ constexpr int CRC_SLICE = 64;   /* bytes per thread in the parallel CRC-16 */
 constexpr int XPOW_HI = 8192;   /* x^(8*256*h) table entries: frames up to 2 MiB */
 constexpr unsigned FULL = 0xffffffffu;
 
+/* Optional per-phase cycle counters (development builds, -DFLACB_PHASE_TIMING): thread 0 of every
+ * CTA adds the cycles between two marks to stats[8 + phase]; tools/perf_sweep.py prints them. */
+#ifdef FLACB_PHASE_TIMING
+#define FLACB_MARK(b, k)                                                      \
+    do {                                                                      \
+        if ((b).tid == 0) {                                                   \
+            const long long t_ = clock64();                                   \
+            atomicAdd(&(b).p.stats[8 + (k)], (u64)(t_ - (b).sh.t_last));      \
+            (b).sh.t_last = t_;                                               \
+        }                                                                     \
+    } while (0)
+#else
+#define FLACB_MARK(b, k) do { } while (0)
+#endif
+
 /* Helpers used from several places stay inline: an out-of-line call forces the per-thread block
  * state (Blk) into local memory, which cost 40 % on the fixed-predictor path when measured. */
 #define FLACB_OUTLINE
@@ -74,7 +89,9 @@ constexpr u64 LB_VALUE = (1ull << 62) - 1;
 __host__ __device__ __forceinline__ uint32_t padidx(uint32_t i) { return i + (i >> 5); }
 
 struct SmemLayout {
-    uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, ldc, qc, total;
+    uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, lpc, lpc_stride, total;
+    /* per-channel LPC front end, offsets inside a channel's lpc area */
+    uint32_t o_autoc, o_levprod, o_ldc, o_qc, o_qmeta, o_fixed;
     uint32_t chan_stride; /* bytes between the residual / running-sum / parameter areas of two channels */
     int xs_all, res_all;
 };
@@ -120,12 +137,22 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     off += l.chan_stride * (l.res_all ? (uint32_t)channels : 1u);
     l.stg = off; off += align16((words + 4) * 4);
     /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
-    uint32_t red_b = align16((MAXB / 32) * RED_STRIDE * 8);
-    const uint32_t pack_b = align16(MAXB * 4) + align16((MAXB + 1) * 4);
+    const uint32_t thr = (uint32_t)((threads + 31) / 32 * 32);
+    uint32_t red_b = align16((thr / 32) * RED_STRIDE * 8);
+    const uint32_t pack_b = align16(thr * 4) + align16((thr + 1) * 4);
     if (red_b < pack_b) red_b = pack_b;
-    l.red = off; l.fb = off; l.pst = off + align16(MAXB * 4); off += red_b;
-    l.ldc = off; off += align16((uint32_t)(L * L) * 8);
-    l.qc = off; off += align16((uint32_t)(L * L) * 4);
+    l.red = off; l.fb = off; l.pst = off + align16(thr * 4); off += red_b;
+    /* LPC front end of every channel (autocorrelation, Levinson and quantised coefficients of
+     * every order, fixed-predictor errors): all channels run their Levinson recursion at once */
+    uint32_t o = 0;
+    l.o_autoc = o; o += align16((uint32_t)(L + 1) * 8);
+    l.o_levprod = o; o += align16((uint32_t)(L > 0 ? L : 1) * 8);
+    l.o_ldc = o; o += align16((uint32_t)(L * L) * 8);
+    l.o_qc = o; o += align16((uint32_t)(L * L) * 4);
+    l.o_qmeta = o; o += align16((uint32_t)(L > 0 ? L : 1) * 16 + 16); /* shift, ncoef, stat, abs per order + lev_stat */
+    l.o_fixed = o; o += 64;
+    l.lpc_stride = o;
+    l.lpc = off; off += o * (uint32_t)channels;
     l.total = off;
     return l;
 }
@@ -176,24 +203,21 @@ struct Decision {
 };
 
 struct Shared {
-    double autoc[FLACB_MAX_LPC + 1];
-    double lev_prod[FLACB_MAX_LPC]; /* coefs[j] * autoc[k+1-j] of the current Levinson step */
-    int32_t qshift[FLACB_MAX_LPC], qncoef[FLACB_MAX_LPC], qstat[FLACB_MAX_LPC];
-    uint32_t qabs[FLACB_MAX_LPC];
     u64 lpc_err[FLACB_MAX_LPC];
-    u64 fixed_err[8];
     u64 qsum[MAX_CAND];
     Decision dec[MAX_CH];
+    int chan_status[MAX_CH]; /* first error of each channel, in the reference's evaluation order */
+    int cur_ch;
     uint32_t cand_o[MAX_CAND], cand_magic[MAX_CAND];
     uint32_t sizeA[MAX_CAND], sizeB[MAX_CAND], any5[MAX_CAND];
     uint32_t errkey;
     int ncand;
-    int lev_stat;
     /* packer */
     uint32_t pos, wbase, crc;
     u64 frame_off;
     uint32_t frame_bytes, payload_bytes;
     int status, writable, range_flag, have_off;
+    long long t_last; /* FLACB_PHASE_TIMING */
     /* where the frame goes (copied from the launch parameters for the out-of-line helpers) */
     uint8_t *o_out;
     u64 o_cap, o_slot_stride;
@@ -220,8 +244,13 @@ struct Blk {
     uint32_t *fb;
     uint32_t *pst;
     u64 *red;
+    /* LPC front end of the current channel (shared memory, see make_layout) */
+    double *autoc, *lev_prod;
     double *ldc;   /* [L][L] Levinson coefficients after iteration k */
     int32_t *qc;   /* [L][L] quantised coefficients per order */
+    int32_t *qshift, *qncoef, *qstat, *lev_stat;
+    uint32_t *qabs;
+    u64 *fixed_err;
     int ldL;       /* row stride of ldc / qc */
     uint32_t stg_words;
     uint32_t wx_bytes; /* bytes of the residual + running-sum area (scratch of the autocorrelation) */
@@ -232,8 +261,10 @@ struct Blk {
 
 __device__ __forceinline__ void set_status(Blk &b, int code)
 {
-    /* first error in the reference's evaluation order wins; callers run in that order */
-    if (b.sh.status == 0) b.sh.status = code;
+    /* first error in the reference's evaluation order wins: per channel in the order of the
+     * stages (callers run in that order), then over the channels in ascending order */
+    int &st = b.sh.chan_status[b.sh.cur_ch];
+    if (st == 0) st = code;
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -456,7 +487,7 @@ __device__ void fixed_errors(Blk &b, const int32_t *x)
             }
         }
     }
-    block_reduce_u64<5>(b, acc, b.sh.fixed_err);
+    block_reduce_u64<5>(b, acc, b.fixed_err);
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -614,7 +645,7 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
             dd_add(S, C, s2);
             C = __dadd_rn(C, c2);
         }
-        if (b.lane == 0) b.sh.autoc[lag] = __dadd_rn(S, C);
+        if (b.lane == 0) b.autoc[lag] = __dadd_rn(S, C);
     }
     __syncthreads();
 }
@@ -634,15 +665,15 @@ __device__ void levinson(Blk &b, int L)
     Shared &sh = b.sh;
     const int lane = b.lane;
     double cj = lane == 0 ? 1.0 : 0.0; /* coefs[lane] */
-    double error = sh.autoc[0];
+    double error = b.autoc[0];
     int stat = 0;
 #pragma unroll 1
     for (int k = 0; k < L; k++) {
-        if (lane <= k) sh.lev_prod[lane] = __dmul_rn(cj, sh.autoc[k + 1 - lane]);
+        if (lane <= k) b.lev_prod[lane] = __dmul_rn(cj, b.autoc[k + 1 - lane]);
         __syncwarp();
         double lambda = 0.0;
 #pragma unroll 4
-        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, sh.lev_prod[j]); /* encoder.py:467 */
+        for (int j = 0; j <= k; j++) lambda = __dsub_rn(lambda, b.lev_prod[j]); /* encoder.py:467 */
         __syncwarp();
         if (error == 0.0) { stat = FLACB_E_ZERODIV; break; }                                /* encoder.py:469 */
         lambda = __ddiv_rn(lambda, error);
@@ -659,7 +690,7 @@ __device__ void levinson(Blk &b, int L)
         if (lane >= 1 && lane <= k + 1) b.ldc[k * b.ldL + lane - 1] = cj;
         if (k + 1 == 32 && lane == 0) b.ldc[k * b.ldL + 31] = c32;
     }
-    if (lane == 0) sh.lev_stat = stat;
+    if (lane == 0) *b.lev_stat = stat;
 }
 
 /* encoder.py:482-534 quantize_lpc_coefficients for order m (one thread per order) */
@@ -674,15 +705,15 @@ __device__ void quantize_order(Blk &b, int m, int precision)
         if (a != a) any_nan = true;
         if (a > cmax) cmax = a;
     }
-    sh.qncoef[m - 1] = 0;
-    sh.qshift[m - 1] = 0;
-    sh.qabs[m - 1] = 0;
-    sh.qstat[m - 1] = 0;
-    if (any_nan || !(cmax > 0.0)) { sh.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:496 */
-    if (isinf(cmax)) { sh.qstat[m - 1] = FLACB_E_OVERFLOW; return; }
+    b.qncoef[m - 1] = 0;
+    b.qshift[m - 1] = 0;
+    b.qabs[m - 1] = 0;
+    b.qstat[m - 1] = 0;
+    if (any_nan || !(cmax > 0.0)) { b.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:496 */
+    if (isinf(cmax)) { b.qstat[m - 1] = FLACB_E_OVERFLOW; return; }
     int shift = precision - ilogb(cmax) - 2; /* floor(log2(cmax)) == exponent, encoder.py:503 */
     if (shift > 15) shift = 15;
-    else if (shift < -16) { sh.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:508 */
+    else if (shift < -16) { b.qstat[m - 1] = FLACB_E_ASSERT; return; } /* encoder.py:508 */
     if (shift < 0) return; /* encoder.py:523-532: loop never appends -> ([], 0) */
     const i64 qmax = ((i64)1 << (precision - 1)) - 1;
     const i64 qmin = -((i64)1 << (precision - 1));
@@ -697,9 +728,9 @@ __device__ void quantize_order(Blk &b, int m, int precision)
         b.qc[(m - 1) * b.ldL + i] = (int32_t)qi;
         asum += (uint32_t)(qi < 0 ? -qi : qi);
     }
-    sh.qncoef[m - 1] = m;
-    sh.qshift[m - 1] = shift;
-    sh.qabs[m - 1] = asum;
+    b.qncoef[m - 1] = m;
+    b.qshift[m - 1] = shift;
+    b.qabs[m - 1] = asum;
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -722,10 +753,10 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
         for (int j = 0; j < LMAX + E; j++) h[j] = i0 < n ? x[padidx((uint32_t)(GUARD + i0 - LMAX + j))] : 0;
 #pragma unroll
         for (int m = 1; m <= LMAX; m++) {
-            if (m <= L && sh.qncoef[m - 1] != 0) {
-                const int shift = sh.qshift[m - 1];
+            if (m <= L && b.qncoef[m - 1] != 0) {
+                const int shift = b.qshift[m - 1];
                 const int32_t *q = b.qc + (m - 1) * b.ldL;
-                const bool small = ((u64)sh.qabs[m - 1] << (b.p.bps - 1)) <= lim32; /* 32-bit sums are exact */
+                const bool small = ((u64)b.qabs[m - 1] << (b.p.bps - 1)) <= lim32; /* 32-bit sums are exact */
                 u64 tot = 0;
                 if (small) {
                     int acc[E];
@@ -1347,8 +1378,26 @@ __device__ int build_frame_header(const EncParams &p, int bs, u64 number, uint8_
 /* ------------------------------------------------------------------------------------- */
 /* the kernel                                                                             */
 
+/* Stage A of a channel: fixed-predictor errors and the autocorrelation (everything the Levinson
+ * recursion needs).  Stage B (analyse_back) follows once every channel's recursion has run. */
 template <int LMAX>
-__device__ void analyse_channel(Blk &b, const int32_t *x, int c)
+__device__ void analyse_front(Blk &b, const int32_t *x)
+{
+    const EncParams &p = b.p;
+    const int L = p.L;
+    FLACB_MARK(b, 0); /* everything before: load, waits */
+    fixed_errors(b, x);
+    FLACB_MARK(b, 1);
+    if (L > 0) {
+        const int bad_win = (b.sh.frame == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail_bad : p.win_full_bad;
+        if (b.tid == 0) *b.lev_stat = bad_win ? FLACB_E_ZERODIV : 0; /* encoder.py:437 */
+        if (!bad_win) autocorrelation<4, (LMAX <= 12 ? 13 : 11)>(b, x, L);
+        FLACB_MARK(b, 2);
+    }
+}
+
+template <int LMAX>
+__device__ void analyse_back(Blk &b, const int32_t *x, int c)
 {
     Shared &sh = b.sh;
     const EncParams &p = b.p;
@@ -1356,32 +1405,14 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
     const int L = p.L;
     Decision &d = sh.dec[c];
     flacb_subframe_info *inf = p.info ? p.info + ((u64)sh.frame * (u64)p.channels + (u64)c) : nullptr;
-
-    fixed_errors(b, x);
     bool lpc_ok = false;
     if (L > 0) {
-        const int bad_win = (sh.frame == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail_bad : p.win_full_bad;
-        if (bad_win) {
-            if (b.tid == 0) set_status(b, FLACB_E_ZERODIV); /* encoder.py:437 */
-        } else {
-            autocorrelation<4, (LMAX <= 12 ? 13 : 11)>(b, x, L);
-            if (b.warp == 0) levinson(b, L);
-            __syncthreads();
-            if (sh.lev_stat == 0) {
-                if (b.tid < L) quantize_order(b, b.tid + 1, p.P);
-                __syncthreads();
-                if (b.tid == 0) {
-                    int st = 0;
-                    for (int m = 0; m < L && st == 0; m++) st = sh.qstat[m];
-                    sh.lev_stat = st;
-                }
-                __syncthreads();
-            }
-            if (sh.lev_stat == 0) {
-                lpc_errors<LMAX>(b, x, L);
-                lpc_ok = true;
-            } else if (b.tid == 0) set_status(b, sh.lev_stat);
-        }
+        if (*b.lev_stat == 0) {
+            FLACB_MARK(b, 4);
+            lpc_errors<LMAX>(b, x, L);
+            FLACB_MARK(b, 5);
+            lpc_ok = true;
+        } else if (b.tid == 0) set_status(b, *b.lev_stat);
         __syncthreads();
     }
     if (b.tid == 0) {
@@ -1389,14 +1420,14 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
         int fo = 0;
         if (n > 4)
             for (int o = 1; o < 5; o++)
-                if (sh.fixed_err[o] < sh.fixed_err[fo]) fo = o;
-        const u64 ftotal = sh.fixed_err[fo];
+                if (b.fixed_err[o] < b.fixed_err[fo]) fo = o;
+        const u64 ftotal = b.fixed_err[fo];
         int lo = 0;
         u64 ltotal = 0;
         if (lpc_ok) {
             for (int m = 1; m <= L; m++) { /* encoder.py:404 first minimum */
                 /* negative-shift quirk: no coefficients -> residual is the signal itself */
-                const u64 t = sh.qncoef[m - 1] ? sh.lpc_err[m - 1] : sh.fixed_err[0];
+                const u64 t = b.qncoef[m - 1] ? sh.lpc_err[m - 1] : b.fixed_err[0];
                 if (m == 1 || t < ltotal) lo = m, ltotal = t;
             }
         }
@@ -1405,7 +1436,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
             if (ltotal < ftotal) use_lpc = true;
             else if (!(ftotal < ltotal)) set_status(b, FLACB_E_ASSERT);
         }
-        if (use_lpc && (lo >= n || sh.qncoef[lo - 1] == 0)) {
+        if (use_lpc && (lo >= n || b.qncoef[lo - 1] == 0)) {
             /* only reachable on tails not longer than the order: the reference then fails in
              * rice_partitions (encoder.py:669) */
             set_status(b, FLACB_E_ASSERT);
@@ -1414,7 +1445,7 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
         d.type = use_lpc ? 1 : 0;
         d.order = use_lpc ? lo : fo;
         d.warm = d.order;
-        d.shift = use_lpc ? sh.qshift[lo - 1] : 0;
+        d.shift = use_lpc ? b.qshift[lo - 1] : 0;
         d.ncoef = use_lpc ? lo : 0;
         if (use_lpc)
             for (int j = 0; j < lo; j++) d.q[j] = b.qc[(lo - 1) * b.ldL + j];
@@ -1426,21 +1457,24 @@ __device__ void analyse_channel(Blk &b, const int32_t *x, int c)
             inf->precision = use_lpc ? p.P : 0;
             inf->fixed_order = fo;
             inf->lpc_order = lpc_ok ? lo : 0;
-            for (int o = 0; o < 5; o++) inf->fixed_err[o] = (n <= 4 && o > 0) ? -1 : (int64_t)sh.fixed_err[o];
+            for (int o = 0; o < 5; o++) inf->fixed_err[o] = (n <= 4 && o > 0) ? -1 : (int64_t)b.fixed_err[o];
             for (int m = 0; m < FLACB_MAX_LPC; m++) {
                 const bool have = lpc_ok && m < L;
-                inf->lpc_err[m] = have ? (int64_t)(sh.qncoef[m] ? sh.lpc_err[m] : sh.fixed_err[0]) : 0;
-                inf->lpc_shift[m] = have ? sh.qshift[m] : 0;
-                inf->lpc_ncoef[m] = have ? sh.qncoef[m] : 0;
-                for (int j = 0; j < FLACB_MAX_LPC; j++) inf->lpc_q[m][j] = (have && j < sh.qncoef[m]) ? b.qc[m * b.ldL + j] : 0;
+                inf->lpc_err[m] = have ? (int64_t)(b.qncoef[m] ? sh.lpc_err[m] : b.fixed_err[0]) : 0;
+                inf->lpc_shift[m] = have ? b.qshift[m] : 0;
+                inf->lpc_ncoef[m] = have ? b.qncoef[m] : 0;
+                for (int j = 0; j < FLACB_MAX_LPC; j++) inf->lpc_q[m][j] = (have && j < b.qncoef[m]) ? b.qc[m * b.ldL + j] : 0;
             }
-            for (int l = 0; l <= FLACB_MAX_LPC; l++) inf->autoc[l] = (L > 0 && l <= L) ? sh.autoc[l] : 0.0;
+            for (int l = 0; l <= FLACB_MAX_LPC; l++) inf->autoc[l] = (L > 0 && l <= L) ? b.autoc[l] : 0.0;
         }
     }
     __syncthreads();
+    FLACB_MARK(b, 6); /* decision */
     residual_and_cum<LMAX>(b, x, d);
+    FLACB_MARK(b, 7);
     uint32_t res_bits;
     rice_search(b, d, &res_bits);
+    FLACB_MARK(b, 8);
     if (b.tid == 0) {
         /* encoder.py:553-627: header byte, warm-up, [precision, shift, coefficients], residual */
         uint32_t bits = 8u + (uint32_t)d.warm * (uint32_t)p.bps + res_bits;
@@ -1477,6 +1511,9 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         sh.frame = p.slot_stride ? blockIdx.x : atomicAdd(p.ticket, 1u);
         sh.status = 0;
         sh.range_flag = 0;
+#ifdef FLACB_PHASE_TIMING
+        sh.t_last = clock64();
+#endif
         sh.o_out = p.out, sh.o_cap = p.out_cap, sh.o_slot_stride = p.slot_stride;
         sh.o_lb_state = p.lb_state, sh.o_frame_off = p.frame_off, sh.o_n_frames = p.n_frames;
         sh.crc = 0;
@@ -1496,29 +1533,86 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     const SmemLayout &lay = p.lay;
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
-    auto select_channel = [&](int c) { /* residual, running sums, Rice parameters of channel c */
+    auto select_channel = [&](int c) { /* per-channel areas: residual, running sums, Rice parameters, LPC front end */
         const uint32_t o = lay.res_all ? (uint32_t)c * lay.chan_stride : 0u;
         b.res = (uint32_t *)(smem + lay.res + o);
         b.cum = (u64 *)(smem + lay.cum + o);
         b.kall = (uint8_t *)(smem + lay.kall + o);
+        unsigned char *q = smem + lay.lpc + (uint32_t)c * lay.lpc_stride;
+        b.autoc = (double *)(q + lay.o_autoc);
+        b.lev_prod = (double *)(q + lay.o_levprod);
+        b.ldc = (double *)(q + lay.o_ldc);
+        b.qc = (int32_t *)(q + lay.o_qc);
+        const int Lq = p.L > 0 ? p.L : 1;
+        b.qshift = (int32_t *)(q + lay.o_qmeta);
+        b.qncoef = b.qshift + Lq;
+        b.qstat = b.qncoef + Lq;
+        b.qabs = (uint32_t *)(b.qstat + Lq);
+        b.lev_stat = (int32_t *)(b.qabs + Lq);
+        b.fixed_err = (u64 *)(q + lay.o_fixed);
+        if (b.tid == 0) sh.cur_ch = c;
     };
-    select_channel(0);
     b.stg = (uint32_t *)(smem + lay.stg);
     b.fb = (uint32_t *)(smem + lay.fb);
     b.pst = (uint32_t *)(smem + lay.pst);
     b.red = (u64 *)(smem + lay.red);
-    b.ldc = (double *)(smem + lay.ldc);
-    b.qc = (int32_t *)(smem + lay.qc);
     b.ldL = p.L;
     b.stg_words = lay.stg_words;
     b.wx_bytes = lay.kall - lay.res;
+    if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
 
     /* ---- phase 0 + 1 ---- */
+    /* stage A of every channel, then the Levinson recursions of all channels side by side (one
+     * warp each: the recursion is a long chain of dependent fp64 operations, 10-20 % of the
+     * frame's time when run per channel), all quantisations in parallel, then stage B */
     if (lay.xs_all) load_planes(b, -1);
-    for (int c = 0; c < p.channels; c++) {
-        if (!lay.xs_all) load_planes(b, c);
-        select_channel(c);
-        analyse_channel<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+    if (p.L == 0) {
+        /* fixed predictors only: nothing to wait for between the two stages */
+        for (int c = 0; c < p.channels; c++) {
+            const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
+            if (!lay.xs_all) load_planes(b, c);
+            select_channel(c);
+            __syncthreads();
+            analyse_front<LMAX>(b, x);
+            analyse_back<LMAX>(b, x, c);
+        }
+    } else {
+        for (int c = 0; c < p.channels; c++) {
+            if (!lay.xs_all) load_planes(b, c);
+            select_channel(c);
+            __syncthreads();
+            analyse_front<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
+        }
+        __syncthreads();
+        for (int c = b.warp; c < p.channels; c += b.nwarps) {
+            select_channel(c); /* warp-local view; cur_ch is not used by the recursion */
+            if (*b.lev_stat == 0) levinson(b, p.L);
+        }
+        __syncthreads();
+        FLACB_MARK(b, 3);
+        for (int idx = b.tid; idx < p.channels * p.L; idx += b.B) {
+            const int c = idx / p.L, m = idx - c * p.L + 1;
+            select_channel(c);
+            if (*b.lev_stat == 0) quantize_order(b, m, p.P);
+        }
+        __syncthreads();
+        if (b.tid < p.channels) { /* first failing order of each channel (encoder.py:378 runs them in order) */
+            select_channel(b.tid);
+            int st = *b.lev_stat;
+            for (int m = 0; m < p.L && st == 0; m++) st = b.qstat[m];
+            *b.lev_stat = st;
+        }
+        __syncthreads();
+        for (int c = 0; c < p.channels; c++) {
+            if (!lay.xs_all && p.channels > 1) load_planes(b, c);
+            select_channel(c);
+            __syncthreads();
+            analyse_back<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+        }
+    }
+    if (b.tid == 0) { /* the frame's status: first failing channel */
+        for (int c = p.channels - 1; c >= 0; c--)
+            if (sh.chan_status[c]) sh.status = sh.chan_status[c];
     }
 
     /* ---- phase 2: frame size -> offset ---- */
@@ -1584,7 +1678,9 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
             }
         }
         __syncthreads();
+        FLACB_MARK(b, 9); /* phase 2, serial header parts, phase-3 recompute */
         pack_residual(b, d);
+        FLACB_MARK(b, 10);
     }
     /* encoder.py:159-165: pad to a byte, CRC-16 over the whole frame, append big endian */
     flush_window(b, sh.payload_bytes - sh.wbase * 4u, (sh.payload_bytes + 3u) >> 2);
@@ -1594,6 +1690,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
             dst[0] = (uint8_t)(sh.crc >> 8);
             dst[1] = (uint8_t)sh.crc;
         }
+        FLACB_MARK(b, 11); /* final flush, CRC-16 */
         p.frame_status[f] = sh.status;
         if (p.stats) {
             for (int c = 0; c < p.channels; c++) {

@@ -83,7 +83,7 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     std::vector<int32_t> frame_status(n_frames, 0);
     std::vector<u64> lb(n_frames, 0);
     uint32_t ticket = 0;
-    u64 dstats[8] = {0};
+    u64 dstats[32] = {0};
     std::vector<uint8_t> slots;
     p.frame_bytes = frame_bytes.data();
     p.frame_off = frame_off.data();
