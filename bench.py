@@ -110,6 +110,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(local_rank: int) -> str:
+    """Best effort: run this rank on the CPUs of the GPU's NUMA node, so that its pinned host
+    buffers (first touch) and the copy threads sit next to the GPU's PCIe root."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"cpus {spec} (NUMA node of GPU {local_rank})"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def peak_hbm() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -188,6 +213,12 @@ def main():
         print(json.dumps(line))
         return
 
+    # Everything but the final JSON line goes to stderr: libraries print banners on fd 1
+    # (NCCL's version line, for one), and the driver reads exactly one JSON line from stdout.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from flac import _native as N
@@ -195,6 +226,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    host_binding = bind_near_gpu(local_rank) if world > 1 else "single rank, not bound"
     sync_t = torch.zeros(1, device=f"cuda:{local_rank}")
 
     def barrier():
@@ -288,6 +320,7 @@ def main():
                        "l2": f"{copies} distinct device copies of input and output rotated between steps "
                              f"({copies * (pcm_bytes + cap) / 1e6:.0f} MB > 126 MB L2)",
                        "sharding": "frame ranges, one rank per GPU, no data-path collective",
+                       "host_binding_rank0": host_binding,
                        "threads_per_frame": st.threads_per_frame, "smem_bytes_per_frame": st.smem_bytes},
             "realtime_x": value * 1e6 / (m["rate"] * ch),
             "compression_ratio": flac_bytes / pcm_bytes,
@@ -310,7 +343,10 @@ def main():
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
