@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -234,6 +234,9 @@ def main():
             dist.all_reduce(sync_t)
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi takes about a second to come up: start it before the synthesis
     raw, m = synth(args.workload, rank, args.seconds)
     ch, bits, bs = m["channels"], m["bits"], m["block"]
     n = m["n"]
@@ -263,9 +266,6 @@ def main():
         return out_len, st
 
     # ---- resident (kernel) measurement ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # nvidia-smi needs a moment to come up: start it before the warm-up
     for k in range(args.warmup):
         out_len, st = step_resident(k)
     barrier()

@@ -48,6 +48,8 @@ struct State {
     int nthreads = 0;
     int bar_count = 0;
     unsigned bar_gen = 0;
+    int nbar_count[16] = {0};
+    unsigned nbar_gen[16] = {0};
     int wbar_count[64];
     unsigned wbar_gen[64];
     unsigned long long wbuf[64][32];
@@ -78,6 +80,20 @@ inline void syncthreads()
         s.bar_gen++;
     } else {
         while (s.bar_gen == g) yield();
+    }
+}
+
+/* bar.sync id, count */
+inline void named_barrier(int id, int count)
+{
+    State &s = st();
+    if (id == 0) return syncthreads();
+    const unsigned g = s.nbar_gen[id];
+    if (++s.nbar_count[id] == count) {
+        s.nbar_count[id] = 0;
+        s.nbar_gen[id]++;
+    } else {
+        while (s.nbar_gen[id] == g) yield();
     }
 }
 
@@ -126,6 +142,7 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
     const size_t stack_bytes = 256 * 1024;
     s.nthreads = nthreads;
     s.bar_count = 0;
+    memset(s.nbar_count, 0, sizeof(s.nbar_count));
     memset(s.wbar_count, 0, sizeof(s.wbar_count));
     s.body = body;
     s.dyn_smem = (unsigned char *)aligned_alloc(128, (dyn_smem_bytes + 127) / 128 * 128 + 128);

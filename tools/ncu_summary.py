@@ -46,7 +46,8 @@ def main():
         if k in hdr:
             print(f"| {k} | {vals[hdr.index(k)]} {units[hdr.index(k)]} |")
     rows = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))))
-    src = open(os.path.join(ROOT, "flac-py_b200", "csrc", src_file)).read().split("\n")
+    src_path = os.environ.get("NCU_SUMMARY_SOURCE", os.path.join(ROOT, "flac-py_b200", "csrc", src_file))
+    src = open(src_path).read().split("\n")  # must be the source the profiled binary was built from
     fn_at, cur = [None] * (len(src) + 2), None
     for i, l in enumerate(src, 1):
         m = re.match(r"^(?:template <[^>]*>\s*)?(?:__device__|__global__|__host__)[^;{]*?\b(\w+)\s*\(", l)
