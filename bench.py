@@ -135,6 +135,15 @@ def bind_near_gpu(local_rank: int) -> str:
     return "not bound"
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return int(json.load(f)[workload]["bytes"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def peak_hbm() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -328,7 +337,7 @@ def main():
             "frames_outside_reference_domain": int(st.out_of_domain),
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "encode_frames_kernel",
+                         "traffic": ncu_traffic(args.workload) if args.seconds is None else None, "peak_source": peak_src, "kernel": "encode_frames_kernel",
                          "kernel_ms": k_ms, "algorithmic_bytes": int(algo),
                          "note": "LPC configs are integer/fp64-ALU bound by the reference's semantics (all orders "
                                  "1..L evaluated): see DESIGN.md"},

@@ -207,11 +207,7 @@ struct Shared {
     u64 qsum[MAX_CAND];
     Decision dec[MAX_CH];
     int chan_status[MAX_CH]; /* first error of each channel, in the reference's evaluation order */
-    /* fixed-predictor subframes prepared while the Levinson recursions run (see the kernel) */
-    int spec_status[MAX_CH];
-    uint32_t spec_bits[MAX_CH];
-    Decision spec[MAX_CH];
-    int spec_valid;
+    int cur_ch;
     uint32_t cand_o[MAX_CAND], cand_magic[MAX_CAND];
     uint32_t sizeA[MAX_CAND], sizeB[MAX_CAND], any5[MAX_CAND];
     uint32_t errkey;
@@ -260,8 +256,6 @@ struct Blk {
     uint32_t wx_bytes; /* bytes of the residual + running-sum area (scratch of the autocorrelation) */
     const double *win;
     int flat_lo, flat_hi;
-    int bar_id, bar_count; /* barrier the block primitives use: 0 = the whole CTA, else a named barrier */
-    int *status_slot;      /* where set_status records this channel's first error */
     __device__ Blk(const EncParams &p_, Shared &sh_) : p(p_), sh(sh_) {}
 };
 
@@ -269,18 +263,8 @@ __device__ __forceinline__ void set_status(Blk &b, int code)
 {
     /* first error in the reference's evaluation order wins: per channel in the order of the
      * stages (callers run in that order), then over the channels in ascending order */
-    if (*b.status_slot == 0) *b.status_slot = code;
-}
-
-/* barrier of the thread group `b` describes: the CTA, or a subset of its warps (named barrier) */
-__device__ __forceinline__ void bsync(const Blk &b)
-{
-#ifdef FLACB_CPU_SIM
-    sim::named_barrier(b.bar_id, b.bar_count);
-#else
-    if (b.bar_id == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(b.bar_id), "r"(b.bar_count) : "memory");
-#endif
+    int &st = b.sh.chan_status[b.sh.cur_ch];
+    if (st == 0) st = code;
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -361,14 +345,14 @@ __device__ u64 block_excl_scan_u64(Blk &b, u64 v, u64 &total)
         if (b.lane >= off) inc += t;
     }
     if (b.lane == 31) b.sh.scan_warp64[b.warp] = inc;
-    bsync(b);
+    __syncthreads();
     u64 base = 0, tot = 0;
     for (int w = 0; w < b.nwarps; w++) {
         u64 x = b.sh.scan_warp64[w];
         if (w < b.warp) base += x;
         tot += x;
     }
-    bsync(b);
+    __syncthreads();
     total = tot;
     return base + inc - v;
 }
@@ -906,9 +890,9 @@ __device__ FLACB_OUTLINE void residual_and_cum(Blk &b, const int32_t *x, const D
         const int G = b.ntiles * b.B; /* run index just behind the last tile */
         if (G * E <= n + E) b.cum[G] = base;
     }
-    bsync(b);
+    __syncthreads();
     if (b.tid == 0 && b.sh.range_flag) set_status(b, FLACB_E_RANGE);
-    bsync(b);
+    __syncthreads();
 }
 
 /* sum of res[0 .. pos) */
@@ -959,7 +943,7 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
         sh.errkey = 0xFFFFFFFFu;
     }
     if (b.tid < MAX_CAND) sh.sizeA[b.tid] = 0, sh.sizeB[b.tid] = 0, sh.any5[b.tid] = 0, sh.qsum[b.tid] = 0;
-    bsync(b);
+    __syncthreads();
     const int ncand = sh.ncand;
     /* parameters of every (order, partition) */
     for (int ci = 0; ci < ncand; ci++) {
@@ -992,7 +976,7 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
             if (f5) atomicOr(&sh.any5[ci], 1u);
         }
     }
-    bsync(b);
+    __syncthreads();
     /* sum over samples of (u >> k) for every candidate order (rice_size, encoder.py:756-760);
      * u >> k < 2^29 for bps <= 24, so a thread's tile sum fits 32 bits */
     u64 lane_q = 0;
@@ -1029,13 +1013,13 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
         if (b.lane == ci) lane_q = t;
     }
     if (b.lane < MAX_CAND) b.red[b.warp * RED_STRIDE + b.lane] = lane_q;
-    bsync(b);
+    __syncthreads();
     if (b.tid < ncand) {
         u64 t = 0;
         for (int w = 0; w < b.nwarps; w++) t += b.red[w * RED_STRIDE + b.tid];
         sh.qsum[b.tid] = t;
     }
-    bsync(b);
+    __syncthreads();
     if (b.tid == 0) {
         int best = 0;
         u64 best_size = 0;
@@ -1049,9 +1033,9 @@ __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
         sh.sizeA[0] = 6u + ((uint32_t)d.method << d.porder) + sh.sizeB[best] + (uint32_t)sh.qsum[best];
         if (sh.errkey != 0xFFFFFFFFu) set_status(b, (int)(sh.errkey & 15u));
     }
-    bsync(b);
+    __syncthreads();
     *res_bits = sh.sizeA[0];
-    bsync(b);
+    __syncthreads();
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -1486,21 +1470,10 @@ __device__ void analyse_back(Blk &b, const int32_t *x, int c)
     }
     __syncthreads();
     FLACB_MARK(b, 6); /* decision */
+    residual_and_cum<LMAX>(b, x, d);
+    FLACB_MARK(b, 7);
     uint32_t res_bits;
-    if (sh.spec_valid && d.type == 0) {
-        /* the fixed predictor won and its subframe is already prepared (same order: both take the
-         * first minimum of the same five sums) */
-        res_bits = sh.spec_bits[c];
-        if (b.tid == 0) {
-            d.porder = sh.spec[c].porder;
-            d.method = sh.spec[c].method;
-            if (sh.spec_status[c]) set_status(b, sh.spec_status[c]);
-        }
-    } else {
-        residual_and_cum<LMAX>(b, x, d);
-        FLACB_MARK(b, 7);
-        rice_search(b, d, &res_bits);
-    }
+    rice_search(b, d, &res_bits);
     FLACB_MARK(b, 8);
     if (b.tid == 0) {
         /* encoder.py:553-627: header byte, warm-up, [precision, shift, coefficients], residual */
@@ -1531,9 +1504,6 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.lane = b.tid & 31;
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;
-    b.bar_id = 0;
-    b.bar_count = b.B;
-    b.status_slot = &sh.chan_status[0];
 
     if (b.tid == 0) {
         /* frames are taken in launch order so that every predecessor of a frame is already
@@ -1580,7 +1550,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         b.qabs = (uint32_t *)(b.qstat + Lq);
         b.lev_stat = (int32_t *)(b.qabs + Lq);
         b.fixed_err = (u64 *)(q + lay.o_fixed);
-        b.status_slot = &sh.chan_status[c];
+        if (b.tid == 0) sh.cur_ch = c;
     };
     b.stg = (uint32_t *)(smem + lay.stg);
     b.fb = (uint32_t *)(smem + lay.fb);
@@ -1590,7 +1560,6 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.stg_words = lay.stg_words;
     b.wx_bytes = lay.kall - lay.res;
     if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
-    if (b.tid == 0) sh.spec_valid = 0;
 
     /* ---- phase 0 + 1 ---- */
     /* stage A of every channel, then the Levinson recursions of all channels side by side (one
@@ -1615,68 +1584,25 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
             analyse_front<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
         }
         __syncthreads();
-        /* One warp per channel runs the Levinson recursion and then quantises every order (lane m
-         * takes order m + 1): a long chain of dependent fp64 operations that keeps a single warp
-         * busy.  When every channel's residual area is resident, the other warps meanwhile prepare
-         * the subframe each channel gets if its fixed predictor wins (residual, running sums, Rice
-         * search) -- which is what happens for most subframes; stage B only redoes that work for
-         * the channels where LPC wins. */
-        const int nlev = p.channels < b.nwarps ? p.channels : b.nwarps;
-        const bool overlap = lay.res_all && b.nwarps >= nlev + 2;
-        if (b.tid == 0) sh.spec_valid = overlap ? 1 : 0;
-        if (b.tid < MAX_CH) sh.spec_status[b.tid] = 0;
-        __syncthreads();
-        if (b.warp < nlev) {
-            for (int c = b.warp; c < p.channels; c += nlev) {
-                select_channel(c);
-                if (*b.lev_stat == 0) {
-                    levinson(b, p.L);
-                    __syncwarp();
-                }
-                if (*b.lev_stat == 0) {
-                    for (int m = b.lane + 1; m <= p.L; m += 32) quantize_order(b, m, p.P);
-                    __syncwarp();
-                    if (b.lane == 0) { /* first failing order (encoder.py:378 runs them in order) */
-                        int st = 0;
-                        for (int m = 0; m < p.L && st == 0; m++) st = b.qstat[m];
-                        *b.lev_stat = st;
-                    }
-                    __syncwarp();
-                }
-            }
-        } else if (overlap) {
-            Blk sb = b; /* the spare warps as a block of their own */
-            sb.tid = b.tid - 32 * nlev;
-            sb.warp = b.warp - nlev;
-            sb.nwarps = b.nwarps - nlev;
-            sb.B = b.B - 32 * nlev;
-            sb.ntiles = (b.n + sb.B * E - 1) / (sb.B * E);
-            sb.bar_id = 1;
-            sb.bar_count = sb.B;
-            for (int c = 0; c < p.channels; c++) {
-                const uint32_t o = (uint32_t)c * lay.chan_stride;
-                sb.res = (uint32_t *)(smem + lay.res + o);
-                sb.cum = (u64 *)(smem + lay.cum + o);
-                sb.kall = (uint8_t *)(smem + lay.kall + o);
-                sb.fixed_err = (u64 *)(smem + lay.lpc + (uint32_t)c * lay.lpc_stride + lay.o_fixed);
-                sb.status_slot = &sh.spec_status[c];
-                Decision &sd = sh.spec[c];
-                if (sb.tid == 0) {
-                    int fo = 0; /* encoder.py:352 first minimum over the fixed orders */
-                    if (b.n > 4)
-                        for (int k = 1; k < 5; k++)
-                            if (sb.fixed_err[k] < sb.fixed_err[fo]) fo = k;
-                    sd.type = 0, sd.order = fo, sd.warm = fo, sd.shift = 0, sd.ncoef = 0;
-                }
-                bsync(sb);
-                residual_and_cum<LMAX>(sb, b.xs + (uint32_t)c * b.xwords, sd);
-                uint32_t bits;
-                rice_search(sb, sd, &bits);
-                if (sb.tid == 0) sh.spec_bits[c] = bits;
-            }
+        for (int c = b.warp; c < p.channels; c += b.nwarps) {
+            select_channel(c); /* warp-local view; cur_ch is not used by the recursion */
+            if (*b.lev_stat == 0) levinson(b, p.L);
         }
         __syncthreads();
         FLACB_MARK(b, 3);
+        for (int idx = b.tid; idx < p.channels * p.L; idx += b.B) {
+            const int c = idx / p.L, m = idx - c * p.L + 1;
+            select_channel(c);
+            if (*b.lev_stat == 0) quantize_order(b, m, p.P);
+        }
+        __syncthreads();
+        if (b.tid < p.channels) { /* first failing order of each channel (encoder.py:378 runs them in order) */
+            select_channel(b.tid);
+            int st = *b.lev_stat;
+            for (int m = 0; m < p.L && st == 0; m++) st = b.qstat[m];
+            *b.lev_stat = st;
+        }
+        __syncthreads();
         for (int c = 0; c < p.channels; c++) {
             if (!lay.xs_all && p.channels > 1) load_planes(b, c);
             select_channel(c);
