@@ -130,13 +130,16 @@ struct BitReader {
     u64 buf;      /* unread bits, left aligned */
     int avail;
     bool eof;
+    uint32_t pre; /* the word at `next`, loaded ahead of its use (state-machine decoder) */
+    bool pre_ok;
 
     __device__ __forceinline__ void init(const uint8_t *s, u64 length, u64 byte_pos)
     {
-        p = s, len = length, next = byte_pos, buf = 0, avail = 0, eof = false;
+        p = s, len = length, next = byte_pos, buf = 0, avail = 0, eof = false, pre = 0, pre_ok = false;
     }
     __device__ __forceinline__ void refill()
     {
+        pre_ok = false; /* reloads from memory whatever had been fetched ahead */
         /* aligned 32-bit loads while a whole word is left (keeps 33..64 bits buffered), single
          * bytes in front of the first aligned word and behind the last one */
         for (;;) {
@@ -351,13 +354,21 @@ __device__ __forceinline__ void lane_fail(LaneState &st, int status)
  * behind the last one.  At most one load per call on the fast path. */
 __device__ __forceinline__ void lane_refill(BitReader &g)
 {
-    if (g.avail <= 32 && g.next + 4 <= g.len && (((uintptr_t)(g.p + g.next)) & 3) == 0) {
-        const uint32_t w = *(const uint32_t *)(g.p + g.next);
-        g.buf |= (u64)__byte_perm(w, 0, 0x0123) << (32 - g.avail);
-        g.avail += 32;
-        g.next += 4;
-    } else if (g.avail <= 32) {
-        g.refill(); /* ends of the stream, unaligned start */
+    if (g.avail <= 32) {
+        if (g.pre_ok) {
+            g.buf |= (u64)__byte_perm(g.pre, 0, 0x0123) << (32 - g.avail);
+            g.avail += 32;
+            g.next += 4;
+            g.pre_ok = false;
+        } else {
+            g.refill(); /* ends of the stream, unaligned start */
+        }
+    }
+    /* fetch the next word now; it is only needed a step or two later, so its latency overlaps the
+     * decoding of the bits already buffered */
+    if (!g.pre_ok && g.next + 4 <= g.len && (((uintptr_t)(g.p + g.next)) & 3) == 0) {
+        g.pre = *(const uint32_t *)(g.p + g.next);
+        g.pre_ok = true;
     }
 }
 

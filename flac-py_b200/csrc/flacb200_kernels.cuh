@@ -75,9 +75,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #define FLACB_MARK(b, k) do { } while (0)
 #endif
 
-/* Helpers used from several places stay inline: an out-of-line call forces the per-thread block
- * state (Blk) into local memory, which cost 40 % on the fixed-predictor path when measured. */
-#define FLACB_OUTLINE
+/* Helpers that take the per-thread block state (Blk) stay inline: an out-of-line call forces that
+ * state into local memory, which cost 40 % on the fixed-predictor path when measured.  The two
+ * helpers that are out of line (flush_window_impl, resolve_offset) take plain arguments. */
 
 /* look-back state flags (top two bits of a 64-bit word, value below) */
 constexpr u64 LB_AGG = 1ull << 62;
@@ -662,7 +662,6 @@ __device__ void levinson(Blk &b, int L)
      * L = 32 and is handled on the side).  The products of the lambda sum are formed in parallel,
      * the sum itself runs in the reference's order (every partial sum is rounded), the symmetric
      * pair update is one step per lane. */
-    Shared &sh = b.sh;
     const int lane = b.lane;
     double cj = lane == 0 ? 1.0 : 0.0; /* coefs[lane] */
     double error = b.autoc[0];
@@ -696,7 +695,6 @@ __device__ void levinson(Blk &b, int L)
 /* encoder.py:482-534 quantize_lpc_coefficients for order m (one thread per order) */
 __device__ void quantize_order(Blk &b, int m, int precision)
 {
-    Shared &sh = b.sh;
     const double *c = b.ldc + (m - 1) * b.ldL;
     double cmax = 0.0;
     bool any_nan = false;
@@ -826,7 +824,7 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
  * running sum cum[g] = sum of res[0 .. g*E) that the Rice search reads partition sums from */
 
 template <int LMAX>
-__device__ FLACB_OUTLINE void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
+__device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
 {
     const int n = b.n;
     u64 base = 0;

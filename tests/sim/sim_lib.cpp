@@ -24,7 +24,7 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
                                 int rice_max, uint64_t first_frame_number, uint32_t flags,
                                 uint8_t *out, uint64_t out_cap, uint64_t *out_len,
                                 uint64_t *frame_offsets, flacb_subframe_info *info,
-                                flacb_stats *stats, int threads_override, uint32_t smem_limit)
+                                flacb_stats *stats, int threads_override, uint32_t plane_mode)
 {
     EncodeArgs a = {n_sample_frames, channels, bits, block_size, max_lpc_order, qlp_precision,
                     rice_min, rice_max, first_frame_number, flags};
@@ -65,14 +65,14 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     window_flat_range(wf, block_size, p.flat_full_lo, p.flat_full_hi);
     window_flat_range(wt, p.tail_size, p.flat_tail_lo, p.flat_tail_hi);
 
-    /* smem_limit here: 0 = the library's own choice of shape; 1 = force the single-plane mode */
+    /* plane_mode: 0 = the library's own choice of shape; 1 = one plane, reloaded per channel; 2 = every plane resident */
     auto layout_total = [&](int threads, int all_planes) {
         return (size_t)make_layout(block_size, channels, bits, rice_max, max_lpc_order, threads, all_planes).total;
     };
     LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total, max_lpc_order > 0);
     if (shape.threads == 0) return FLACB_E_UNSUPPORTED;
-    if (smem_limit == 1) shape.all_planes = 0;
-    if (smem_limit == 2) shape.all_planes = 1;
+    if (plane_mode == 1) shape.all_planes = 0;
+    if (plane_mode == 2) shape.all_planes = 1;
     const int B = threads_override ? threads_override : shape.threads;
     const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, shape.all_planes);
     p.all_planes = shape.all_planes;

@@ -116,7 +116,7 @@ def pack_pcm(pcm: np.ndarray, bits: int) -> np.ndarray:
 def encode_frames(pcm: np.ndarray, bits: int, block_size: int, max_lpc_order: int = 12,
                   qlp_precision: int = 5, rice_min: int = 0, rice_max: int = 5,
                   first_frame_number: int = 0, flags: int = 0, want_info: bool = False,
-                  threads: int = 0, smem_limit: int = 0, int32_input: bool = False,
+                  threads: int = 0, plane_mode: int = 0, int32_input: bool = False,
                   small_window: bool = False):
     """-> (status, data, frame_offsets, info list | None, Stats)"""
     n, ch = pcm.shape
@@ -136,7 +136,7 @@ def encode_frames(pcm: np.ndarray, bits: int, block_size: int, max_lpc_order: in
     rc = lib(small_window).flacb_sim_encode(raw.ctypes.data, n, ch, bits, block_size, max_lpc_order,
                                 qlp_precision, rice_min, rice_max, first_frame_number, flags,
                                 out.ctypes.data, cap, C.byref(out_len), offs.ctypes.data, info,
-                                C.byref(st), threads, smem_limit)
+                                C.byref(st), threads, plane_mode)
     return rc, out[:out_len.value].tobytes(), offs, (list(info)[:nfr * ch] if info else None), st
 
 

@@ -31,10 +31,10 @@ def test_sim_slot_mode_and_single_plane_mode(name):
     ref = case_stream(case)[42:]
     rc, data, _, _, _ = simlib.encode_frames(x, case["bits"], flags=simlib.FLAG_SLOT_COMPACT, **case_kwargs(case))
     assert rc == 0 and data == ref
-    # one channel plane in shared memory, reloaded per channel and phase (smem_limit=1), and
-    # every plane resident (smem_limit=2)
+    # one channel plane in shared memory, reloaded per channel and phase (plane_mode=1), and
+    # every plane resident (plane_mode=2)
     for mode in (1, 2):
-        rc, data, _, _, st = simlib.encode_frames(x, case["bits"], smem_limit=mode, **case_kwargs(case))
+        rc, data, _, _, st = simlib.encode_frames(x, case["bits"], plane_mode=mode, **case_kwargs(case))
         assert rc == 0 and data == ref, mode
 
 
