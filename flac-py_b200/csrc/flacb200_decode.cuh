@@ -305,15 +305,18 @@ __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Can
  * in ST_RICE (one Rice code per step, at most one refill per step), so the warp stays
  * converged; header fields, warm-up samples, partition parameters are rare steps. */
 
-struct History { /* last 32 reconstructed samples, circular (LPC subframes) */
-    i64 h[32];
+/* Last 32 reconstructed samples, circular (LPC subframes).  Kept as int32: the samples of a valid
+ * stream fit (the decoder's output is int32 anyway), and for the garbage "frames" behind false
+ * sync candidates any value will do. */
+struct History {
+    int32_t h[32];
     int head;
-    __device__ __forceinline__ void push(i64 v)
+    __device__ __forceinline__ void push(int32_t v)
     {
         h[head & 31] = v;
         head++;
     }
-    __device__ __forceinline__ i64 back(int j) const { return h[(head - 1 - j) & 31]; } /* x[i-1-j] */
+    __device__ __forceinline__ int32_t back(int j) const { return h[(head - 1 - j) & 31]; } /* x[i-1-j] */
 };
 
 enum {
@@ -340,7 +343,7 @@ struct LaneState {
     int pos, idx;                         /* sample position in the subframe; warm-up / coef index */
     int method, porder, parts_left, part_left, k, esc_size;
     u64 cnt;                              /* zeros of an unfinished unary run */
-    i64 x1, x2, x3, x4;                   /* last four samples (fixed predictors, common.py:15-21) */
+    int32_t x1, x2, x3, x4;               /* last four samples (fixed predictors, common.py:15-21) */
     int32_t *out;                         /* this channel's plane in the scratch area */
 };
 
@@ -374,25 +377,27 @@ __device__ __forceinline__ void lane_refill(BitReader &g)
 
 __device__ __forceinline__ void lane_store(LaneState &st, History &hist, const int32_t *coef, i64 r)
 {
-    /* prediction restore of decoder.py:493-498 on the fly */
-    i64 v;
+    /* prediction restore of decoder.py:493-498 on the fly.  Sums of the fixed predictors wrap
+     * modulo 2^32, which leaves the stored low 32 bits exact; the LPC sum needs 64 bits because
+     * of the shift. */
+    int32_t v;
     if (st.type <= 12) {
         const int o = st.order;
-        const i64 pred = o == 0 ? 0 : o == 1 ? st.x1 : o == 2 ? 2 * st.x1 - st.x2
-                         : o == 3 ? 3 * st.x1 - 3 * st.x2 + st.x3 : 4 * st.x1 - 6 * st.x2 + 4 * st.x3 - st.x4;
-        v = r + pred;
+        const int32_t pred = o == 0 ? 0 : o == 1 ? st.x1 : o == 2 ? 2 * st.x1 - st.x2
+                             : o == 3 ? 3 * st.x1 - 3 * st.x2 + st.x3 : 4 * st.x1 - 6 * st.x2 + 4 * st.x3 - st.x4;
+        v = (int32_t)((uint32_t)r + (uint32_t)pred);
     } else {
         i64 acc = 0;
-        for (int j = 0; j < st.order; j++) acc += hist.back(j) * (i64)coef[j];
-        v = r + (acc >> (st.shift < 0 ? 0 : st.shift));
+        for (int j = 0; j < st.order; j++) acc += (i64)hist.back(j) * (i64)coef[j];
+        v = (int32_t)(r + (acc >> (st.shift < 0 ? 0 : st.shift)));
         hist.push(v);
     }
     st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = v;
-    st.out[st.pos++] = (int32_t)v;
+    st.out[st.pos++] = v;
     if (--st.part_left == 0) st.state = st.parts_left > 0 ? ST_PART_HDR : ST_SUB_HDR + 100; /* 100+: subframe done */
 }
 
-__device__ void lane_step(LaneState &st, History &hist, int32_t *coef, int32_t *tmp, u64 tmp_off)
+__device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t *coef, int32_t *tmp, u64 tmp_off)
 {
     BitReader &g = st.g;
     switch (st.state) {
@@ -466,8 +471,8 @@ __device__ void lane_step(LaneState &st, History &hist, int32_t *coef, int32_t *
         lane_refill(g);
         const i64 v = g.read_signed(st.ss);
         if (g.eof) return lane_fail(st, FLACB_E_EOF);
-        hist.push(v);
-        st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = v;
+        hist.push((int32_t)v);
+        st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = (int32_t)v;
         st.out[st.idx++] = (int32_t)v;
         st.pos = st.idx;
         break;

@@ -42,7 +42,9 @@ def decode_frames_status(frames, sample_size: int, *, devices: Optional[Sequence
     front of the first one the reference decoder fails in, and that failure's status."""
     raw = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else frames
     ctx = N.default_context(devices[0] if devices else None)
-    cap = cap_sample_frames * 8 if cap_sample_frames else max(raw.size * 16, 1 << 16)
+    # room for the decoded samples: STREAMINFO's count when the caller knows it (times the most
+    # channels a frame can carry), else a generous guess that is grown on demand
+    cap = (cap_sample_frames + 65536) * 8 if cap_sample_frames else max(raw.size * 16, 1 << 16)
     while True:
         out = np.empty(cap, dtype=np.int32)
         rc, n, fch, _ = ctx.decode_raw(raw.ctypes.data if raw.size else 0, raw.size, sample_size, 0,
@@ -77,7 +79,8 @@ def decode(buffer: BufferedIOBase) -> tuple[int, int, int, int, Iterator[list[in
     def samples() -> Iterator[list[int]]:
         # like the reference's generator: the sample frames of the good frames first, then the
         # exception of the frame that fails
-        pcm, _, rc = decode_frames_status(buffer.read(), streaminfo.sample_size)
+        pcm, _, rc = decode_frames_status(buffer.read(), streaminfo.sample_size,
+                                          cap_sample_frames=streaminfo.samples or None)
         for row in pcm.tolist():
             yield row
         N.raise_for_status(rc, "decode")
@@ -94,5 +97,5 @@ def decode_pcm(buffer: BufferedIOBase) -> tuple[Streaminfo, np.ndarray]:
     streaminfo = get_metadata_block_streaminfo(get)
     if header.last is False:
         skip_metadata(get)
-    pcm, _ = decode_frames(buffer.read(), streaminfo.sample_size)
+    pcm, _ = decode_frames(buffer.read(), streaminfo.sample_size, cap_sample_frames=streaminfo.samples or None)
     return streaminfo, pcm

@@ -167,3 +167,16 @@ def test_chunked_host_pipeline_matches_single_launch(monkeypatch):
     sh, _ = _encode(y, 16, p)
     assert sh.rc == N.E_ZERODIV and sh.stats.first_bad_frame == 50
     assert sh.out.tobytes() == O.encode_frames(y[:4608 * 50], 16, 4608, 12, 5, 0, 5, threads=8).data
+
+
+def test_sharding_over_two_gpus_in_one_process():
+    """encode_pcm(devices=[0, 1]): frame ranges on two GPUs from two host threads, byte ranges
+    concatenated on the host"""
+    from flac import _native as N
+    if N.lib().flacb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from flac.encoder import encode_pcm
+    case = CASES["many_frames"]
+    x = case_pcm(case)
+    stream = b"".join(encode_pcm(case["rate"], case["bits"], 2, S.pack_le(x, 16), _params(case), devices=[0, 1]))
+    assert stream == case_stream(case)
