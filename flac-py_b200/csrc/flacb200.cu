@@ -710,8 +710,13 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     if ((rc = c->d_frames.ensure((tmp_samples + 16) * 4))) return rc;
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
-    decode_frames_kernel<<<(unsigned)((n_cand + 31) / 32), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand,
-                                                                               d_tmpoff, d_tmp, check_crc8);
+    int lanes = DECODE_LANES;
+    if (const char *e = getenv("FLACB200_DECODE_LANES")) { /* tuning knob */
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) lanes = v;
+    }
+    decode_frames_kernel<<<(unsigned)((n_cand + lanes - 1) / lanes), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand, d_tmpoff,
+                                                                                         d_tmp, check_crc8, lanes);
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -587,10 +587,14 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
     }
 }
 
+/* frames per warp: fewer than 32 trades idle lanes for less divergence between the lanes' states
+ * and more warps per SM (the kernel is bound by the latency of one warp's instruction stream) */
+constexpr int DECODE_LANES = 8; /* default; the launch passes the value in use */
+
 __global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
-                                                           const u64 *tmp_off, int32_t *tmp, int filter)
+                                                           const u64 *tmp_off, int32_t *tmp, int filter, int lanes)
 {
-    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ci = (int)threadIdx.x < lanes ? blockIdx.x * (uint32_t)lanes + threadIdx.x : n_cand;
     LaneState st;
     History hist;
     int32_t coef[FLACB_MAX_LPC];
