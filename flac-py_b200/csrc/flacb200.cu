@@ -10,11 +10,12 @@
 #include <string.h>
 
 #include <atomic>
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "flacb200_host.h"
-#include "flacb200_kernels.cuh"
+#include "flacb200_launch.h"
 #include "flacb200_decode.cuh"
 
 using namespace flacb;
@@ -84,7 +85,7 @@ struct HostBuf {
 struct EncSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
-    DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info;
+    DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info, pre, dec;
     HostBuf h_meta;
     bool d2h_pending = false;
 };
@@ -158,19 +159,20 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     }
     CUDA_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1>));
-    c->static_smem12 = fa.sharedSizeBytes;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, encode_frames_kernel<32, 576, 1>));
-    c->static_smem32 = fa.sharedSizeBytes;
-    /* CRC-16 tables (crc.py:4-14) and the x^n weights of the parallel CRC */
+    c->static_smem12 = static_smem_12_fused();
+    c->static_smem32 = static_smem_32_fused();
+    if (static_smem_12_staged() > c->static_smem12) c->static_smem12 = static_smem_12_staged();
+    if (static_smem_32_staged() > c->static_smem32) c->static_smem32 = static_smem_32_staged();
+    /* CRC-16 tables (crc.py:4-14) and the x^n weights of the parallel CRC, once per kernel
+     * translation unit */
     uint16_t tab[256], lo[256];
     std::vector<uint16_t> hi(XPOW_HI);
     crc16_table(tab);
     crc16_xpow_tables(lo, hi.data(), XPOW_HI);
-    CUDA_TRY(cudaMemcpyToSymbol(c_crc16_tab, tab, sizeof(tab)));
-    CUDA_TRY(cudaMemcpyToSymbol(c_xpow_lo, lo, sizeof(lo)));
-    CUDA_TRY(cudaMemcpyToSymbol(c_xpow_hi, hi.data(), sizeof(uint16_t) * XPOW_HI));
+    CUDA_TRY(init_12_fused(tab, lo, hi.data()));
+    CUDA_TRY(init_12_staged(tab, lo, hi.data()));
+    CUDA_TRY(init_32_fused(tab, lo, hi.data()));
+    CUDA_TRY(init_32_staged(tab, lo, hi.data()));
     CUDA_TRY(cudaDeviceSynchronize());
     *out = c;
     return FLACB_OK;
@@ -185,7 +187,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < FLACB_SLOTS; i++) {
         EncSlot &sl = c->slot[i];
-        DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.frame_off, &sl.status, &sl.lb, &sl.misc, &sl.info};
+        DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.frame_off, &sl.status, &sl.lb, &sl.misc, &sl.info, &sl.pre, &sl.dec};
         for (DevBuf *b : sb) b->release();
         sl.h_meta.release();
         cudaEvent_t se[] = {sl.ev_k0, sl.ev_k1, sl.ev_c0, sl.ev_c1, sl.ev_d0, sl.ev_d1};
@@ -296,7 +298,24 @@ struct EncPlan {
     LaunchShape shape;
     bool lmax12;
     size_t static_smem;
+    /* staged: analyse_kernel -> lpc_coefficients_kernel -> choose_kernel -> encode_frames_kernel<.., 2>
+     * (split_back == false: choice and serialisation in one kernel, encode_frames_kernel<.., 1>) */
+    bool staged, split_back;
+    LaunchShape front;  /* shape of analyse_kernel */
+    LaunchShape choose; /* shape of choose_kernel */
 };
+
+/* "threads,all_planes,variant" tuning knobs */
+static void shape_from_env(const char *name, LaunchShape &sh, size_t static_smem, size_t smem_optin,
+                           const std::function<size_t(int, int)> &layout_total)
+{
+    const char *e = getenv(name);
+    if (!e) return;
+    int t = 0, ap = 1, v = 0;
+    if (sscanf(e, "%d,%d,%d", &t, &ap, &v) == 3 && t >= 32 && t % 32 == 0 && t <= (v ? 288 : 576) &&
+        layout_total(t, ap) + static_smem <= smem_optin)
+        sh.threads = t, sh.all_planes = ap, sh.variant = v;
+}
 
 static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
 {
@@ -309,11 +328,43 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
     };
     plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total, a.max_lpc_order > 0);
     if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
-    if (const char *e = getenv("FLACB200_SHAPE")) { /* tuning knob: "threads,all_planes,variant" */
-        int t = 0, ap = 1, v = 0;
-        if (sscanf(e, "%d,%d,%d", &t, &ap, &v) == 3 && t >= 32 && t % 32 == 0 && t <= (v ? 288 : 576) &&
-            layout_total(t, ap) + plan.static_smem <= (size_t)c->smem_optin)
-            plan.shape.threads = t, plan.shape.all_planes = ap, plan.shape.variant = v;
+    shape_from_env("FLACB200_SHAPE", plan.shape, plan.static_smem, (size_t)c->smem_optin, layout_total);
+    plan.staged = a.max_lpc_order > 0 && !(a.flags & FLACB_FUSED) && !getenv("FLACB200_FUSED");
+    plan.split_back = !getenv("FLACB200_NO_SPLIT_BACK");
+    if (plan.staged) {
+        /* stages A and C1: as many resident frames as the registers allow (three at 72), every
+         * plane resident when that does not cost a frame */
+        auto small_shape = [&](const std::function<size_t(int, int)> &total, LaunchShape &out) {
+            LaunchShape f = {pick_threads(a.block_size, E, 288), 0, 0, 1};
+            for (int ap = 1; ap >= 0; ap--) {
+                const size_t dyn = total(f.threads, ap);
+                if (dyn + plan.static_smem > (size_t)c->smem_optin) continue;
+                int ctas = (int)((228 * 1024) / (dyn + plan.static_smem + 1024));
+                const int by_regs = 65536 / (72 * f.threads);
+                if (ctas > by_regs) ctas = by_regs;
+                if (ctas > f.ctas_per_sm) f.all_planes = ap, f.ctas_per_sm = ctas;
+            }
+            out = f;
+            return f.ctas_per_sm > 0;
+        };
+        auto front_total = [&](int threads, int all_planes) {
+            return (size_t)make_layout_front(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
+        };
+        auto choose_total = [&](int threads, int all_planes) {
+            return (size_t)make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
+        };
+        if (!small_shape(front_total, plan.front) || !small_shape(choose_total, plan.choose)) plan.staged = false;
+        shape_from_env("FLACB200_SHAPE_A", plan.front, plan.static_smem, (size_t)c->smem_optin, front_total);
+        shape_from_env("FLACB200_SHAPE_C1", plan.choose, plan.static_smem, (size_t)c->smem_optin, choose_total);
+    }
+    if (plan.staged && plan.split_back) {
+        /* stage C2 needs no LPC front end in shared memory: the shape of the fixed-only path */
+        auto back_total = [&](int threads, int all_planes) {
+            return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, 0, threads, all_planes).total;
+        };
+        plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, back_total, 0);
+        if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED;
+        shape_from_env("FLACB200_SHAPE_C2", plan.shape, plan.static_smem, (size_t)c->smem_optin, back_total);
     }
     return FLACB_OK;
 }
@@ -326,7 +377,11 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     const int tail = full_tail ? a.block_size : (int)(a.n_sample_frames - (n_frames - 1) * (u64)a.block_size);
     const LaunchShape &shape = plan.shape;
     const int B = shape.threads;
-    const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, shape.all_planes);
+    const bool split_back = plan.staged && plan.split_back;
+    /* stage C2 carries no LPC front end in shared memory */
+    const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, split_back ? 0 : a.max_lpc_order, B,
+                                       shape.all_planes);
+    const SmemLayout lay_rec = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, 0); /* record offsets */
 
     int rc; /* the window tables were uploaded by the caller before the first chunk */
     if ((rc = sl.frame_bytes.ensure(n_frames * 4))) return rc;
@@ -380,22 +435,50 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         p.out_cap = out_cap;
     }
 
+    const u64 n_sub = n_frames * (u64)a.channels;
+    if (plan.staged) {
+        p.pre_stride = (lay_rec.lpc_stride + 15u) & ~15u;
+        if ((rc = sl.pre.ensure(n_sub * (u64)p.pre_stride))) return rc;
+        p.pre = (uint8_t *)sl.pre.p;
+        if (split_back) {
+            if ((rc = sl.dec.ensure(n_sub * sizeof(SubDecision)))) return rc;
+            p.dec = (SubDecision *)sl.dec.p;
+        }
+    }
+    auto launch = [&](int kind, int variant, int threads, size_t smem, const EncParams &kp) {
+        g_launches++;
+        if (plan.lmax12) return plan.staged ? launch_12_staged(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp)
+                                            : launch_12_fused(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp);
+        return plan.staged ? launch_32_staged(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp)
+                           : launch_32_fused(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp);
+    };
+
     CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 512, sl.stream));
     CUDA_TRY(cudaMemsetAsync(sl.lb.p, 0, n_frames * 8, sl.stream));
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
-#define FLACB_LAUNCH(LM, TB, MB)                                                                                   \
-    do {                                                                                                           \
-        CUDA_TRY(cudaFuncSetAttribute(encode_frames_kernel<LM, TB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)lay.total));                                                            \
-        encode_frames_kernel<LM, TB, MB><<<(unsigned)n_frames, B, lay.total, sl.stream>>>(p);                     \
-    } while (0)
-    if (plan.lmax12 && shape.variant) FLACB_LAUNCH(12, 288, 3);
-    else if (plan.lmax12) FLACB_LAUNCH(12, 576, 1);
-    else if (shape.variant) FLACB_LAUNCH(32, 288, 3);
-    else FLACB_LAUNCH(32, 576, 1);
-#undef FLACB_LAUNCH
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
+    if (plan.staged) {
+        EncParams pa = p;
+        pa.lay = make_layout_front(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.front.threads,
+                                   plan.front.all_planes);
+        pa.all_planes = plan.front.all_planes;
+        CUDA_TRY(launch(K_ANALYSE, plan.front.variant, plan.front.threads, pa.lay.total, pa));
+        const int wpb = 4; /* subframes (warps) per CTA of stage B */
+        const size_t smem_b = (size_t)wpb * p.pre_stride;
+        EncParams pb = p;
+        pb.lay = lay_rec;
+        CUDA_TRY(cudaFuncSetAttribute(lpc_coefficients_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        lpc_coefficients_kernel<<<(unsigned)((n_sub + wpb - 1) / wpb), wpb * 32, smem_b, sl.stream>>>(pb, (uint32_t)n_sub);
+        CUDA_TRY(cudaGetLastError());
+        g_launches++;
+        if (split_back) {
+            EncParams pc = p;
+            pc.lay = make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.choose.threads,
+                                        plan.choose.all_planes);
+            pc.all_planes = plan.choose.all_planes;
+            CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
+        }
+    }
+    CUDA_TRY(launch(plan.staged ? (split_back ? K_SERIALISE : K_BACK) : K_FUSED, shape.variant, B, lay.total, p));
     if (a.flags & FLACB_SLOT_COMPACT) {
         scan_frame_bytes_kernel<<<1, 256, 0, sl.stream>>>(p.frame_bytes, p.frame_off, p.n_frames);
         CUDA_TRY(cudaGetLastError());

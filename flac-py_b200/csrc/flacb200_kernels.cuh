@@ -157,6 +157,58 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     return l;
 }
 
+/* Shared memory plan of analyse_kernel (stage A of the staged pipeline): sample planes, the
+ * windowed samples of the two tapered ends, per-warp partial sums.  Only the fields that
+ * fixed_errors / autocorrelation read are filled; the o_* offsets and lpc_stride describe the
+ * per-subframe record in HBM and equal make_layout's. */
+__host__ __device__ inline SmemLayout make_layout_front(int nmax, int channels, int bps, int rmax, int L, int threads,
+                                                         int all_planes)
+{
+    SmemLayout l = make_layout(nmax, channels, bps, rmax, L, threads, 0);
+    l.xs_all = all_planes >= 1;
+    l.res_all = 0;
+    const uint32_t plane = align16(l.xwords * 4);
+    uint32_t off = 0;
+    l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
+    /* both tapered ends of a Tukey(0.5) window: n/2 + 152 samples at most (autocorrelation()
+     * computes on the fly if a window ever needs more) */
+    const uint32_t cnt = nmax >= 1024 ? (uint32_t)nmax / 2 + 256 : (uint32_t)nmax + 160;
+    const uint32_t wx_b = align16((cnt + (cnt >> 3) + 2) * 8);
+    l.res = off; l.cum = off; l.kall = off + wx_b; /* wx_bytes = kall - res */
+    l.chan_stride = wx_b;
+    off += wx_b;
+    const uint32_t autoc_words = (uint32_t)((threads + 31) / 32) * (FLACB_MAX_LPC + 1) * 6 + 8;
+    l.stg_words = autoc_words;
+    l.stg = off; off += align16((autoc_words + 4) * 4);
+    const uint32_t thr = (uint32_t)((threads + 31) / 32 * 32);
+    l.red = off; l.fb = off; l.pst = off; off += align16((thr / 32) * RED_STRIDE * 8);
+    l.lpc = off; /* no LPC area in shared memory: the records live in HBM */
+    l.total = off;
+    return l;
+}
+
+/* Shared memory plan of choose_kernel (stage C1): sample planes, reduction scratch and the
+ * coefficient records of the frame's subframes. */
+__host__ __device__ inline SmemLayout make_layout_choose(int nmax, int channels, int bps, int rmax, int L, int threads,
+                                                          int all_planes)
+{
+    SmemLayout l = make_layout(nmax, channels, bps, rmax, L, threads, 0);
+    l.xs_all = all_planes >= 1;
+    l.res_all = 0;
+    const uint32_t plane = align16(l.xwords * 4);
+    uint32_t off = 0;
+    l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
+    l.res = l.cum = l.kall = l.stg = off;
+    l.stg_words = 0;
+    const uint32_t thr = (uint32_t)((threads + 31) / 32 * 32);
+    l.red = off; l.fb = off; l.pst = off; off += align16((thr / 32) * RED_STRIDE * 8);
+    l.lpc = off; off += l.lpc_stride * (uint32_t)channels;
+    l.total = off;
+    return l;
+}
+
+struct SubDecision;
+
 struct EncParams {
     const uint8_t *pcm;        /* interleaved, cbytes per sample, little endian */
     u64 n_sample_frames;
@@ -183,14 +235,21 @@ struct EncParams {
     flacb_subframe_info *info; /* optional, device memory */
     int all_planes;            /* every channel plane resident in shared memory */
     SmemLayout lay;            /* make_layout(...) of this launch, computed once on the host */
+    /* staged pipeline (analyse_kernel -> lpc_coefficients_kernel -> encode_frames_kernel<.., true>):
+     * per subframe one "LPC front end" record in HBM, laid out like the shared-memory one
+     * (lay.o_autoc .. lay.lpc_stride), pre_stride bytes apart */
+    uint8_t *pre;
+    uint32_t pre_stride;
+    SubDecision *dec;          /* [n_frames * channels] choices of choose_kernel for encode_frames_kernel<.., 2> */
 };
 
 #ifndef FLACB_HOST_ONLY
 
 /* CRC-16 helper tables: x^(8*l) mod P for l < 256 and x^(8*256*h) mod P (P = 0x18005) */
-__constant__ uint16_t c_xpow_lo[256];
-__constant__ uint16_t c_xpow_hi[XPOW_HI];
-__constant__ uint16_t c_crc16_tab[256];
+/* (one copy per translation unit: flacb200_launch.h) */
+static __constant__ uint16_t c_xpow_lo[256];
+static __constant__ uint16_t c_xpow_hi[XPOW_HI];
+static __constant__ uint16_t c_crc16_tab[256];
 
 struct Decision {
     int32_t type;   /* 0 fixed, 1 lpc */
@@ -200,6 +259,12 @@ struct Decision {
     int32_t porder, method;
     uint32_t bits;  /* serialised subframe size */
     int32_t q[FLACB_MAX_LPC];
+};
+
+/* what choose_kernel hands to the serialising kernel for one subframe */
+struct SubDecision {
+    Decision d;
+    int32_t status;
 };
 
 struct Shared {
@@ -315,7 +380,7 @@ __device__ void block_reduce_u64(Blk &b, u64 (&v)[K], u64 *out)
     __syncthreads();
 }
 
-__device__ uint32_t block_excl_scan_u32(Blk &b, uint32_t v, uint32_t &total)
+static __device__ uint32_t block_excl_scan_u32(Blk &b, uint32_t v, uint32_t &total)
 {
     uint32_t inc = v;
 #pragma unroll
@@ -336,7 +401,7 @@ __device__ uint32_t block_excl_scan_u32(Blk &b, uint32_t v, uint32_t &total)
     return base + inc - v;
 }
 
-__device__ u64 block_excl_scan_u64(Blk &b, u64 v, u64 &total)
+static __device__ u64 block_excl_scan_u64(Blk &b, u64 v, u64 &total)
 {
     u64 inc = v;
 #pragma unroll
@@ -465,7 +530,7 @@ __device__ __forceinline__ void fixed_residuals(const int (&a)[E + 4], int e, in
     r[4] = x0 - 4 * x1 + 6 * x2 - 4 * x3 + x4;
 }
 
-__device__ void fixed_errors(Blk &b, const int32_t *x)
+static __device__ void fixed_errors(Blk &b, const int32_t *x)
 {
     u64 acc[5] = {0, 0, 0, 0, 0};
     for (int tile = 0; tile < b.ntiles; tile++) {
@@ -656,7 +721,7 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
  * order; `lambda ** 2` is evaluated as lambda*lambda (glibc pow differs by 1 ulp on ~0.08% of
  * arguments; documented in DESIGN.md).  One warp.                                            */
 
-__device__ void levinson(Blk &b, int L)
+static __device__ void levinson(Blk &b, int L)
 {
     /* warp 0: lane j keeps coefs[j] (j < 32; coefs[32] only appears in the last iteration of
      * L = 32 and is handled on the side).  The products of the lambda sum are formed in parallel,
@@ -693,7 +758,7 @@ __device__ void levinson(Blk &b, int L)
 }
 
 /* encoder.py:482-534 quantize_lpc_coefficients for order m (one thread per order) */
-__device__ void quantize_order(Blk &b, int m, int precision)
+static __device__ void quantize_order(Blk &b, int m, int precision)
 {
     const double *c = b.ldc + (m - 1) * b.ldL;
     double cmax = 0.0;
@@ -914,7 +979,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t i, uint32_t d, uint32_t ma
  * Returns through d.porder / d.method and the exact number of residual bits in *res_bits.
  * keep_params: leave kall[] valid for the chosen order (phase 3).                           */
 
-__device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
+static __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
 {
     Shared &sh = b.sh;
     const EncParams &p = b.p;
@@ -1066,7 +1131,7 @@ __device__ __forceinline__ uint32_t gf16_mul(uint32_t a, uint32_t bb)
 /* phase 2, deferred: byte offset of this frame = sum of the sizes of all frames in front of it.
  * Decoupled look-back, one warp, 32 predecessors per probe: sizes are summed backwards until a
  * frame that already knows its own inclusive prefix is met. */
-__device__ __noinline__ void resolve_offset(Shared *shp, int tid)
+static __device__ __noinline__ void resolve_offset(Shared *shp, int tid)
 {
     /* out of line and on plain arguments: called from every flush site, and a reference to the
      * per-thread block state would force that state into local memory */
@@ -1131,7 +1196,7 @@ __device__ __noinline__ void resolve_offset(Shared *shp, int tid)
  * zero init and no final xor, crc(A || B) = crc(A) * x^(8|B|) + crc(B), so a slice's CRC times
  * x^(8 * bytes behind it) can simply be xor-ed into the frame's.  Then the window is rebased at
  * word `wend` (the partial word, if any, moves to the front). */
-__device__ __noinline__ void flush_window_impl(Shared *shp, uint32_t *stg, uint32_t stg_words, int tid, int B,
+static __device__ __noinline__ void flush_window_impl(Shared *shp, uint32_t *stg, uint32_t stg_words, int tid, int B,
                                               uint32_t nbytes, uint32_t wend)
 {
     Shared &sh = *shp;
@@ -1234,7 +1299,7 @@ struct Packer {
  * of its E consecutive samples into registers; the words strictly inside its bit range are
  * plain shared-memory stores, the first word (shared with the previous thread) is handed to the
  * thread that owns it, and each owner ors the pieces of its last word together.  No atomics. */
-__device__ void pack_residual(Blk &b, const Decision &d)
+static __device__ void pack_residual(Blk &b, const Decision &d)
 {
     Shared &sh = b.sh;
     const int n = b.n;
@@ -1326,7 +1391,7 @@ __device__ void pack_residual(Blk &b, const Decision &d)
 /* ------------------------------------------------------------------------------------- */
 /* encoder.py:194-234 put_frame_header (+ coded_number.py:7-39, crc.py:17-22)              */
 
-__device__ int build_frame_header(const EncParams &p, int bs, u64 number, uint8_t *h)
+static __device__ int build_frame_header(const EncParams &p, int bs, u64 number, uint8_t *h)
 {
     int code = 0, extra = 0;
     switch (bs) { /* common.py:85-105 */
@@ -1394,8 +1459,9 @@ __device__ void analyse_front(Blk &b, const int32_t *x)
     }
 }
 
+/* encoder.py:387-404, :135-157: error of every LPC order, best order, fixed-vs-LPC choice */
 template <int LMAX>
-__device__ void analyse_back(Blk &b, const int32_t *x, int c)
+__device__ void analyse_choose(Blk &b, const int32_t *x, int c)
 {
     Shared &sh = b.sh;
     const EncParams &p = b.p;
@@ -1468,6 +1534,16 @@ __device__ void analyse_back(Blk &b, const int32_t *x, int c)
     }
     __syncthreads();
     FLACB_MARK(b, 6); /* decision */
+}
+
+/* winner's residual, Rice partition search, exact subframe size (encoder.py:632-760) */
+template <int LMAX>
+__device__ void analyse_size(Blk &b, const int32_t *x, int c)
+{
+    Shared &sh = b.sh;
+    const EncParams &p = b.p;
+    Decision &d = sh.dec[c];
+    flacb_subframe_info *inf = p.info ? p.info + ((u64)sh.frame * (u64)p.channels + (u64)c) : nullptr;
     residual_and_cum<LMAX>(b, x, d);
     FLACB_MARK(b, 7);
     uint32_t res_bits;
@@ -1489,9 +1565,187 @@ __device__ void analyse_back(Blk &b, const int32_t *x, int c)
     __syncthreads();
 }
 
-/* TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
- * <288, 3> (72 registers) where three frames fit an SM. */
+template <int LMAX>
+__device__ __forceinline__ void analyse_back(Blk &b, const int32_t *x, int c)
+{
+    analyse_choose<LMAX>(b, x, c);
+    analyse_size<LMAX>(b, x, c);
+}
+
+/* point the LPC front-end views of the block state at one record (shared memory or HBM) */
+__device__ __forceinline__ void bind_lpc_record(Blk &b, unsigned char *q, const SmemLayout &lay, int L)
+{
+    b.autoc = (double *)(q + lay.o_autoc);
+    b.lev_prod = (double *)(q + lay.o_levprod);
+    b.ldc = (double *)(q + lay.o_ldc);
+    b.qc = (int32_t *)(q + lay.o_qc);
+    const int Lq = L > 0 ? L : 1;
+    b.qshift = (int32_t *)(q + lay.o_qmeta);
+    b.qncoef = b.qshift + Lq;
+    b.qstat = b.qncoef + Lq;
+    b.qabs = (uint32_t *)(b.qstat + Lq);
+    b.lev_stat = (int32_t *)(b.qabs + Lq);
+    b.fixed_err = (u64 *)(q + lay.o_fixed);
+}
+
+/* Levinson recursion and quantisation of one subframe by one warp (lane m-1 quantises order m),
+ * then the first failing order (encoder.py:378 runs the orders in turn) */
+static __device__ void lpc_coefficients_warp(Blk &b, int L, int P)
+{
+    if (*b.lev_stat == 0) levinson(b, L);
+    __syncwarp();
+    if (*b.lev_stat == 0)
+        for (int m = b.lane + 1; m <= L; m += 32) quantize_order(b, m, P);
+    __syncwarp();
+    if (b.lane == 0) {
+        int st = *b.lev_stat;
+        for (int m = 0; m < L && st == 0; m++) st = b.qstat[m];
+        *b.lev_stat = st;
+    }
+    __syncwarp();
+}
+
+/* ---- staged pipeline, stage A: fixed-predictor errors and autocorrelation of every subframe of
+ * a frame -> the subframe's record in HBM.  Small shared-memory footprint (planes, windowed
+ * ends), no packer state: more frames per SM than the full kernel. */
 template <int LMAX, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
+{
+    FLACB_DYN_SMEM(smem);
+    __shared__ Shared sh;
+    Blk b(p, sh);
+    b.tid = (int)threadIdx.x;
+    b.B = (int)blockDim.x;
+    b.lane = b.tid & 31;
+    b.warp = b.tid >> 5;
+    b.nwarps = b.B >> 5;
+    const uint32_t f = blockIdx.x;
+    if (b.tid == 0) {
+        sh.frame = f;
+#ifdef FLACB_PHASE_TIMING
+        sh.t_last = clock64();
+#endif
+    }
+    __syncthreads();
+    b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
+    b.ntiles = (b.n + b.B * E - 1) / (b.B * E);
+    const bool tail_frame = f == p.n_frames - 1 && p.tail_size != p.block_size;
+    b.win = tail_frame ? p.win_tail : p.win_full;
+    b.flat_lo = tail_frame ? p.flat_tail_lo : p.flat_full_lo;
+    b.flat_hi = tail_frame ? p.flat_tail_hi : p.flat_full_hi;
+    const SmemLayout &lay = p.lay;
+    b.xs = (int32_t *)(smem + lay.xs);
+    b.xwords = lay.xwords;
+    b.res = (uint32_t *)(smem + lay.res);
+    b.cum = (u64 *)(smem + lay.cum);
+    b.kall = (uint8_t *)(smem + lay.kall);
+    b.stg = (uint32_t *)(smem + lay.stg);
+    b.fb = (uint32_t *)(smem + lay.fb);
+    b.pst = (uint32_t *)(smem + lay.pst);
+    b.red = (u64 *)(smem + lay.red);
+    b.ldL = p.L;
+    b.stg_words = lay.stg_words;
+    b.wx_bytes = lay.kall - lay.res;
+    if (lay.xs_all) load_planes(b, -1);
+    for (int c = 0; c < p.channels; c++) {
+        if (!lay.xs_all) load_planes(b, c);
+        bind_lpc_record(b, p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride, lay, p.L);
+        __syncthreads();
+        analyse_front<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
+    }
+}
+
+/* ---- stage C1: error of every LPC order on every sample, best order, fixed-vs-LPC choice
+ * (encoder.py:387-404, :135-157) -> one SubDecision per subframe in HBM.  Same small footprint
+ * as stage A plus the subframes' coefficient records; its code is the unrolled all-orders
+ * filter and little else, so the instruction cache holds it. */
+template <int LMAX, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
+{
+    FLACB_DYN_SMEM(smem);
+    __shared__ Shared sh;
+    Blk b(p, sh);
+    b.tid = (int)threadIdx.x;
+    b.B = (int)blockDim.x;
+    b.lane = b.tid & 31;
+    b.warp = b.tid >> 5;
+    b.nwarps = b.B >> 5;
+    const uint32_t f = blockIdx.x;
+    if (b.tid == 0) {
+        sh.frame = f;
+#ifdef FLACB_PHASE_TIMING
+        sh.t_last = clock64();
+#endif
+    }
+    if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
+    b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
+    b.ntiles = (b.n + b.B * E - 1) / (b.B * E);
+    const SmemLayout &lay = p.lay;
+    b.xs = (int32_t *)(smem + lay.xs);
+    b.xwords = lay.xwords;
+    b.red = (u64 *)(smem + lay.red);
+    b.ldL = p.L;
+    /* the records of this frame's subframes (autocorrelation only for the introspection record) */
+    for (int c = 0; c < p.channels; c++) {
+        const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
+        uint32_t *loc = (uint32_t *)(smem + lay.lpc + (uint32_t)c * lay.lpc_stride);
+        for (uint32_t i = (uint32_t)b.tid; i < lay.o_levprod / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+        for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.tid; i < lay.lpc_stride / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+    }
+    if (lay.xs_all) load_planes(b, -1);
+    else __syncthreads();
+    for (int c = 0; c < p.channels; c++) {
+        if (!lay.xs_all) load_planes(b, c);
+        bind_lpc_record(b, smem + lay.lpc + (uint32_t)c * lay.lpc_stride, lay, p.L);
+        if (b.tid == 0) sh.cur_ch = c;
+        __syncthreads();
+        analyse_choose<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+        SubDecision *out = p.dec + ((u64)f * (u64)p.channels + (u64)c);
+        const uint32_t *src = (const uint32_t *)&sh.dec[c];
+        for (uint32_t i = (uint32_t)b.tid; i < sizeof(Decision) / 4; i += (uint32_t)b.B) ((uint32_t *)&out->d)[i] = src[i];
+        if (b.tid == 0) out->status = sh.chan_status[c];
+    }
+}
+
+/* ---- stage B: Levinson-Durbin and coefficient quantisation, one warp per subframe.  The
+ * recursion is a chain of dependent fp64 operations: in the one-kernel design a frame's other
+ * warps waited for it (a fifth of the frame's time); here every subframe of the launch runs its
+ * chain at once and nobody waits. */
+#ifndef FLACB_TU_KERNELS_ONLY /* the non-template kernels are defined once, in flacb200.cu */
+__global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p, uint32_t n_sub)
+{
+    FLACB_DYN_SMEM(smem);
+    __shared__ Shared sh;
+    Blk b(p, sh);
+    b.tid = (int)threadIdx.x;
+    b.B = (int)blockDim.x;
+    b.lane = b.tid & 31;
+    b.warp = b.tid >> 5;
+    b.nwarps = b.B >> 5;
+    b.ldL = p.L;
+    const SmemLayout &lay = p.lay;
+    const uint32_t s = blockIdx.x * (uint32_t)b.nwarps + (uint32_t)b.warp;
+    if (s >= n_sub) return;
+    uint32_t *rec = (uint32_t *)(p.pre + (u64)s * (u64)p.pre_stride);
+    uint32_t *loc = (uint32_t *)(smem + (uint32_t)b.warp * p.pre_stride);
+    /* in: autocorrelation and status; out: everything behind the Levinson matrix */
+    for (uint32_t i = (uint32_t)b.lane; i < lay.o_levprod / 4; i += 32) loc[i] = rec[i];
+    bind_lpc_record(b, (unsigned char *)loc, lay, p.L);
+    if (b.lane == 0) *b.lev_stat = *(int32_t *)((unsigned char *)rec + ((unsigned char *)b.lev_stat - (unsigned char *)loc));
+    __syncwarp();
+    lpc_coefficients_warp(b, p.L, p.P);
+    for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.lane; i < lay.o_fixed / 4; i += 32) rec[i] = loc[i];
+}
+#endif
+
+/* TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
+ * <288, 3> (72 registers) where three frames fit an SM.
+ * MODE 0: everything in this kernel.  MODE 1: stage C of the staged pipeline -- the LPC front
+ * end of every subframe (fixed errors, quantised coefficients of every order) is read from its
+ * record in HBM instead of being computed here.  MODE 2: stage C2 -- the choice of every
+ * subframe was made by choose_kernel as well; this kernel computes the winner's residual, the
+ * Rice partitions and the bytes. */
+template <int LMAX, int TB, int MINB, int MODE>
 __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
@@ -1536,18 +1790,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         b.res = (uint32_t *)(smem + lay.res + o);
         b.cum = (u64 *)(smem + lay.cum + o);
         b.kall = (uint8_t *)(smem + lay.kall + o);
-        unsigned char *q = smem + lay.lpc + (uint32_t)c * lay.lpc_stride;
-        b.autoc = (double *)(q + lay.o_autoc);
-        b.lev_prod = (double *)(q + lay.o_levprod);
-        b.ldc = (double *)(q + lay.o_ldc);
-        b.qc = (int32_t *)(q + lay.o_qc);
-        const int Lq = p.L > 0 ? p.L : 1;
-        b.qshift = (int32_t *)(q + lay.o_qmeta);
-        b.qncoef = b.qshift + Lq;
-        b.qstat = b.qncoef + Lq;
-        b.qabs = (uint32_t *)(b.qstat + Lq);
-        b.lev_stat = (int32_t *)(b.qabs + Lq);
-        b.fixed_err = (u64 *)(q + lay.o_fixed);
+        bind_lpc_record(b, smem + lay.lpc + (uint32_t)c * lay.lpc_stride, lay, p.L);
         if (b.tid == 0) sh.cur_ch = c;
     };
     b.stg = (uint32_t *)(smem + lay.stg);
@@ -1564,7 +1807,37 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
      * warp each: the recursion is a long chain of dependent fp64 operations, 10-20 % of the
      * frame's time when run per channel), all quantisations in parallel, then stage B */
     if (lay.xs_all) load_planes(b, -1);
-    if (p.L == 0) {
+    if constexpr (MODE == 2) {
+        for (uint32_t i = (uint32_t)b.tid; i < (uint32_t)p.channels * (sizeof(Decision) / 4); i += (uint32_t)b.B) {
+            const uint32_t c = i / (uint32_t)(sizeof(Decision) / 4), k = i - c * (uint32_t)(sizeof(Decision) / 4);
+            ((uint32_t *)&sh.dec[c])[k] = ((const uint32_t *)&p.dec[(u64)f * (u64)p.channels + c].d)[k];
+        }
+        __syncthreads(); /* chan_status was zeroed above */
+        if (b.tid < p.channels) sh.chan_status[b.tid] = p.dec[(u64)f * (u64)p.channels + (u64)b.tid].status;
+        for (int c = 0; c < p.channels; c++) {
+            if (!lay.xs_all && (p.channels > 1 || c == 0)) load_planes(b, c);
+            select_channel(c);
+            __syncthreads();
+            analyse_size<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+        }
+    } else if constexpr (MODE == 1) {
+        /* the records of this frame's subframes: autocorrelation (for the introspection
+         * record), quantised coefficients, per-order meta data, fixed errors */
+        for (int c = 0; c < p.channels; c++) {
+            const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
+            uint32_t *loc = (uint32_t *)(smem + lay.lpc + (uint32_t)c * lay.lpc_stride);
+            for (uint32_t i = (uint32_t)b.tid; i < lay.o_levprod / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+            for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.tid; i < lay.lpc_stride / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+        }
+        __syncthreads();
+        for (int c = 0; c < p.channels; c++) {
+            if (!lay.xs_all && (p.channels > 1 || c == 0)) load_planes(b, c);
+            select_channel(c);
+            __syncthreads();
+            analyse_back<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+        }
+    } else {
+      if (p.L == 0) {
         /* fixed predictors only: nothing to wait for between the two stages */
         for (int c = 0; c < p.channels; c++) {
             const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
@@ -1607,6 +1880,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
             __syncthreads();
             analyse_back<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
         }
+      }
     }
     if (b.tid == 0) { /* the frame's status: first failing channel */
         for (int c = p.channels - 1; c >= 0; c--)
@@ -1703,6 +1977,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
 /* ------------------------------------------------------------------------------------- */
 /* slot mode (debugging aid): exclusive scan of frame sizes and compaction                 */
 
+#ifndef FLACB_TU_KERNELS_ONLY
 __global__ void scan_frame_bytes_kernel(const uint32_t *frame_bytes, u64 *frame_off, uint32_t n)
 {
     /* single CTA, n is small (frames of one call) */
@@ -1747,6 +2022,7 @@ __global__ void compact_slots_kernel(const uint8_t *slots, u64 slot_stride, cons
     const uint8_t *src = slots + (u64)f * slot_stride;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) out[off + i] = src[i];
 }
+#endif
 
 #endif /* !FLACB_HOST_ONLY */
 

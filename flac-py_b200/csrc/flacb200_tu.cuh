@@ -1,0 +1,75 @@
+/*
+ * flacb200_tu.cuh -- body of the four kernel translation units: instantiates the encode kernels
+ * for FLACB_TU_LMAX (unroll depth of the LPC loops) and FLACB_TU_STAGED (0: the one-kernel path,
+ * 1: the staged pipeline) and defines their launchers (flacb200_launch.h).
+ */
+#define FLACB_TU_KERNELS_ONLY 1
+#include "flacb200_launch.h"
+
+namespace flacb {
+
+#define FLACB_CAT_(a, b) a##b
+#define FLACB_CAT(a, b) FLACB_CAT_(a, b)
+#if FLACB_TU_STAGED
+#define FLACB_TU_NAME FLACB_CAT(FLACB_TU_LMAX, _staged)
+#else
+#define FLACB_TU_NAME FLACB_CAT(FLACB_TU_LMAX, _fused)
+#endif
+
+template <class K>
+static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem, cudaStream_t stream, const EncParams &p)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, threads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, unsigned grid, int threads, size_t smem,
+                                               cudaStream_t stream, const EncParams &p)
+{
+    constexpr int LM = FLACB_TU_LMAX;
+#if FLACB_TU_STAGED
+    switch (kind) {
+    case K_ANALYSE:
+        return variant ? launch_one(analyse_kernel<LM, 288, 3>, grid, threads, smem, stream, p)
+                       : launch_one(analyse_kernel<LM, 576, 1>, grid, threads, smem, stream, p);
+    case K_CHOOSE:
+        return variant ? launch_one(choose_kernel<LM, 288, 3>, grid, threads, smem, stream, p)
+                       : launch_one(choose_kernel<LM, 576, 1>, grid, threads, smem, stream, p);
+    case K_SERIALISE:
+        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 2>, grid, threads, smem, stream, p)
+                       : launch_one(encode_frames_kernel<LM, 576, 1, 2>, grid, threads, smem, stream, p);
+    case K_BACK:
+        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 1>, grid, threads, smem, stream, p)
+                       : launch_one(encode_frames_kernel<LM, 576, 1, 1>, grid, threads, smem, stream, p);
+    default: return cudaErrorInvalidValue;
+    }
+#else
+    if (kind != K_FUSED) return cudaErrorInvalidValue;
+    return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 0>, grid, threads, smem, stream, p)
+                   : launch_one(encode_frames_kernel<LM, 576, 1, 0>, grid, threads, smem, stream, p);
+#endif
+}
+
+/* the __constant__ tables of flacb200_kernels.cuh exist once per translation unit */
+cudaError_t FLACB_CAT(init_, FLACB_TU_NAME)(const uint16_t *crc_tab, const uint16_t *xpow_lo, const uint16_t *xpow_hi)
+{
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_crc16_tab, crc_tab, sizeof(uint16_t) * 256)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_xpow_lo, xpow_lo, sizeof(uint16_t) * 256)) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_xpow_hi, xpow_hi, sizeof(uint16_t) * XPOW_HI);
+}
+
+size_t FLACB_CAT(static_smem_, FLACB_TU_NAME)()
+{
+    cudaFuncAttributes fa;
+#if FLACB_TU_STAGED
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, 2>) != cudaSuccess) return 8192;
+#else
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, 0>) != cudaSuccess) return 8192;
+#endif
+    return fa.sharedSizeBytes;
+}
+
+} /* namespace flacb */

@@ -23,6 +23,7 @@ OUTPUT_ON_DEVICE = 0x04
 LENIENT = 0x08
 SLOT_COMPACT = 0x10
 PCM_INT32 = 0x20
+FUSED = 0x40  # the whole LPC encode in one kernel per frame instead of the staged pipeline (same bytes)
 
 MAX_LPC = 32
 INFO_PARAMS = 64

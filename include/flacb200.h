@@ -54,6 +54,9 @@ enum {
                                        wins ties.  Frames concerned are counted in the stats.     */
 #define FLACB_SLOT_COMPACT    0x10u /* debugging: per-frame worst-case slots + compaction kernel
                                        instead of the single-pass look-back placement            */
+#define FLACB_FUSED           0x40u /* debugging / comparison: the whole LPC encode in one kernel
+                                       per frame instead of the staged pipeline (analysis ->
+                                       coefficients -> choice + serialisation); same bytes       */
 #define FLACB_PCM_INT32       0x20u /* samples are int32 containers (whatever `bits` is); default
                                        is the WAV payload layout, ceil(bits/8) LE bytes/sample    */
 

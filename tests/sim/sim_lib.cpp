@@ -71,8 +71,8 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     };
     LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total, max_lpc_order > 0);
     if (shape.threads == 0) return FLACB_E_UNSUPPORTED;
-    if (plane_mode == 1) shape.all_planes = 0;
-    if (plane_mode == 2) shape.all_planes = 1;
+    if ((plane_mode & 0xFFu) == 1) shape.all_planes = 0;
+    if ((plane_mode & 0xFFu) == 2) shape.all_planes = 1;
     const int B = threads_override ? threads_override : shape.threads;
     const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, shape.all_planes);
     p.all_planes = shape.all_planes;
@@ -102,11 +102,64 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         p.out = out;
         p.out_cap = out_cap;
     }
+    const bool staged = max_lpc_order > 0 && !(flags & FLACB_FUSED);
+    /* bit 8 of plane_mode: choice and serialisation in one kernel (encode_frames_kernel<.., 1>) */
+    const bool split_back = staged && !(plane_mode & 0x100u);
+    std::vector<uint8_t> pre;
+    std::vector<SubDecision> dec;
+    if (staged) {
+        /* stages A, B (and C1) of the staged pipeline, same sequence as flacb200.cu */
+        p.pre_stride = (lay.lpc_stride + 15u) & ~15u;
+        const uint64_t n_sub = n_frames * (uint64_t)channels;
+        pre.assign(n_sub * p.pre_stride, 0xA5);
+        p.pre = pre.data();
+        EncParams pa = p;
+        const int front_planes = (plane_mode & 0xFFu) == 1 ? 0 : 1;
+        pa.lay = make_layout_front(block_size, channels, bits, rice_max, max_lpc_order, B, front_planes);
+        pa.all_planes = front_planes;
+        for (uint64_t f = 0; f < n_frames; f++) {
+            if (max_lpc_order <= 12)
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<12, 576, 1>(pa); });
+            else
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<32, 576, 1>(pa); });
+        }
+        const int wpb = 4;
+        const unsigned nb = (unsigned)((n_sub + wpb - 1) / wpb);
+        for (unsigned blk = 0; blk < nb; blk++)
+            sim::run_block(blk, nb, wpb * 32, (size_t)wpb * p.pre_stride, [&]() { lpc_coefficients_kernel(p, (uint32_t)n_sub); });
+        if (split_back) {
+            dec.resize(n_sub);
+            memset(dec.data(), 0xA5, n_sub * sizeof(SubDecision));
+            p.dec = dec.data();
+            EncParams pc = p;
+            pc.lay = make_layout_choose(block_size, channels, bits, rice_max, max_lpc_order, B, front_planes);
+            pc.all_planes = front_planes;
+            for (uint64_t f = 0; f < n_frames; f++) {
+                if (max_lpc_order <= 12)
+                    sim::run_block((unsigned)f, (unsigned)n_frames, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1>(pc); });
+                else
+                    sim::run_block((unsigned)f, (unsigned)n_frames, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1>(pc); });
+            }
+            /* stage C2 carries no LPC front end in shared memory */
+            p.lay = make_layout(block_size, channels, bits, rice_max, 0, B, shape.all_planes);
+        }
+    }
+    const size_t dyn = p.lay.total;
     for (uint64_t f = 0; f < n_frames; f++) {
-        if (max_lpc_order <= 12)
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<12, 576, 1>(p); });
+        if (split_back) {
+            if (max_lpc_order <= 12)
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 2>(p); });
+            else
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 2>(p); });
+        } else if (staged) {
+            if (max_lpc_order <= 12)
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 1>(p); });
+            else
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 1>(p); });
+        } else if (max_lpc_order <= 12)
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 0>(p); });
         else
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, lay.total, [&]() { encode_frames_kernel<32, 576, 1>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 0>(p); });
     }
     if (flags & FLACB_SLOT_COMPACT) {
         sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(frame_bytes.data(), frame_off.data(), (uint32_t)n_frames); });

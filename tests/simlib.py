@@ -23,6 +23,7 @@ FLAG_SPEC_CHANNELS = 0x01
 FLAG_LENIENT = 0x08
 FLAG_SLOT_COMPACT = 0x10
 FLAG_PCM_INT32 = 0x20
+FLAG_FUSED = 0x40
 
 
 class Stats(C.Structure):

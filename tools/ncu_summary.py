@@ -50,7 +50,7 @@ def main():
     src = open(src_path).read().split("\n")  # must be the source the profiled binary was built from
     fn_at, cur = [None] * (len(src) + 2), None
     for i, l in enumerate(src, 1):
-        m = re.match(r"^(?:template <[^>]*>\s*)?(?:__device__|__global__|__host__)[^;{]*?\b(\w+)\s*\(", l)
+        m = re.match(r"^(?:template <[^>]*>\s*)?(?:static )?(?:__device__|__global__|__host__)[^;{]*?\b(\w+)\s*\(", l)
         if m and not l.strip().endswith(";"):
             cur = m.group(1)
         fn_at[i] = cur
