@@ -85,6 +85,8 @@ struct HostBuf {
 struct EncSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    cudaEvent_t ev_s[3] = {nullptr, nullptr, nullptr}; /* between the stages of the LPC pipeline */
+    bool staged = false;
     DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info, pre, dec;
     HostBuf h_meta;
     bool d2h_pending = false;
@@ -154,25 +156,23 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
         EncSlot &sl = c->slot[i];
         if (i == 0) sl.stream = c->stream;
         else CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        cudaEvent_t *se[] = {&sl.ev_k0, &sl.ev_k1, &sl.ev_c0, &sl.ev_c1, &sl.ev_d0, &sl.ev_d1};
+        cudaEvent_t *se[] = {&sl.ev_k0, &sl.ev_k1, &sl.ev_c0, &sl.ev_c1, &sl.ev_d0, &sl.ev_d1, &sl.ev_s[0], &sl.ev_s[1], &sl.ev_s[2]};
         for (cudaEvent_t *e : se) CUDA_TRY(cudaEventCreate(e));
     }
     CUDA_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    c->static_smem12 = static_smem_12_fused();
-    c->static_smem32 = static_smem_32_fused();
-    if (static_smem_12_staged() > c->static_smem12) c->static_smem12 = static_smem_12_staged();
-    if (static_smem_32_staged() > c->static_smem32) c->static_smem32 = static_smem_32_staged();
+    c->static_smem12 = static_smem_12();
+    c->static_smem32 = static_smem_32();
+    if (static_smem_fixed() > c->static_smem12) c->static_smem12 = static_smem_fixed();
     /* CRC-16 tables (crc.py:4-14) and the x^n weights of the parallel CRC, once per kernel
      * translation unit */
     uint16_t tab[256], lo[256];
     std::vector<uint16_t> hi(XPOW_HI);
     crc16_table(tab);
     crc16_xpow_tables(lo, hi.data(), XPOW_HI);
-    CUDA_TRY(init_12_fused(tab, lo, hi.data()));
-    CUDA_TRY(init_12_staged(tab, lo, hi.data()));
-    CUDA_TRY(init_32_fused(tab, lo, hi.data()));
-    CUDA_TRY(init_32_staged(tab, lo, hi.data()));
+    CUDA_TRY(init_fixed(tab, lo, hi.data()));
+    CUDA_TRY(init_12(tab, lo, hi.data()));
+    CUDA_TRY(init_32(tab, lo, hi.data()));
     CUDA_TRY(cudaDeviceSynchronize());
     *out = c;
     return FLACB_OK;
@@ -190,7 +190,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
         DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.frame_off, &sl.status, &sl.lb, &sl.misc, &sl.info, &sl.pre, &sl.dec};
         for (DevBuf *b : sb) b->release();
         sl.h_meta.release();
-        cudaEvent_t se[] = {sl.ev_k0, sl.ev_k1, sl.ev_c0, sl.ev_c1, sl.ev_d0, sl.ev_d1};
+        cudaEvent_t se[] = {sl.ev_k0, sl.ev_k1, sl.ev_c0, sl.ev_c1, sl.ev_d0, sl.ev_d1, sl.ev_s[0], sl.ev_s[1], sl.ev_s[2]};
         for (cudaEvent_t e : se)
             if (e) cudaEventDestroy(e);
         if (i > 0 && sl.stream) cudaStreamDestroy(sl.stream);
@@ -295,12 +295,12 @@ struct ChunkMeta {
 };
 
 struct EncPlan {
-    LaunchShape shape;
+    LaunchShape shape;  /* the serialising kernel (encode_frames_kernel) */
     bool lmax12;
     size_t static_smem;
-    /* staged: analyse_kernel -> lpc_coefficients_kernel -> choose_kernel -> encode_frames_kernel<.., 2>
-     * (split_back == false: choice and serialisation in one kernel, encode_frames_kernel<.., 1>) */
-    bool staged, split_back;
+    /* LPC configurations: analyse_kernel -> lpc_coefficients_kernel -> choose_kernel ->
+     * encode_frames_kernel<.., true>; fixed predictors only: encode_frames_kernel<.., false> */
+    bool staged;
     LaunchShape front;  /* shape of analyse_kernel */
     LaunchShape choose; /* shape of choose_kernel */
 };
@@ -323,14 +323,14 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
     plan.static_smem = plan.lmax12 ? c->static_smem12 : c->static_smem32;
     if ((size_t)c->smem_optin <= plan.static_smem + 1024) return FLACB_E_UNSUPPORTED;
     if (frame_bound(a.block_size, a.channels, a.bits, a.rice_max) >= (u64)XPOW_HI * 256) return FLACB_E_UNSUPPORTED;
+    /* the serialising kernel carries no LPC front end in shared memory */
     auto layout_total = [&](int threads, int all_planes) {
-        return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
+        return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, 0, threads, all_planes).total;
     };
-    plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total, a.max_lpc_order > 0);
+    plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, layout_total);
     if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
     shape_from_env("FLACB200_SHAPE", plan.shape, plan.static_smem, (size_t)c->smem_optin, layout_total);
-    plan.staged = a.max_lpc_order > 0 && !(a.flags & FLACB_FUSED) && !getenv("FLACB200_FUSED");
-    plan.split_back = !getenv("FLACB200_NO_SPLIT_BACK");
+    plan.staged = a.max_lpc_order > 0;
     if (plan.staged) {
         /* stages A and C1: as many resident frames as the registers allow (three at 72), every
          * plane resident when that does not cost a frame */
@@ -353,18 +353,9 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
         auto choose_total = [&](int threads, int all_planes) {
             return (size_t)make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
         };
-        if (!small_shape(front_total, plan.front) || !small_shape(choose_total, plan.choose)) plan.staged = false;
+        if (!small_shape(front_total, plan.front) || !small_shape(choose_total, plan.choose)) return FLACB_E_UNSUPPORTED;
         shape_from_env("FLACB200_SHAPE_A", plan.front, plan.static_smem, (size_t)c->smem_optin, front_total);
         shape_from_env("FLACB200_SHAPE_C1", plan.choose, plan.static_smem, (size_t)c->smem_optin, choose_total);
-    }
-    if (plan.staged && plan.split_back) {
-        /* stage C2 needs no LPC front end in shared memory: the shape of the fixed-only path */
-        auto back_total = [&](int threads, int all_planes) {
-            return (size_t)make_layout(a.block_size, a.channels, a.bits, a.rice_max, 0, threads, all_planes).total;
-        };
-        plan.shape = pick_shape(a.block_size, E, plan.static_smem, (size_t)c->smem_optin, 228 * 1024, back_total, 0);
-        if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED;
-        shape_from_env("FLACB200_SHAPE_C2", plan.shape, plan.static_smem, (size_t)c->smem_optin, back_total);
     }
     return FLACB_OK;
 }
@@ -377,10 +368,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     const int tail = full_tail ? a.block_size : (int)(a.n_sample_frames - (n_frames - 1) * (u64)a.block_size);
     const LaunchShape &shape = plan.shape;
     const int B = shape.threads;
-    const bool split_back = plan.staged && plan.split_back;
-    /* stage C2 carries no LPC front end in shared memory */
-    const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, split_back ? 0 : a.max_lpc_order, B,
-                                       shape.all_planes);
+    const SmemLayout lay = make_layout(a.block_size, a.channels, a.bits, a.rice_max, 0, B, shape.all_planes);
     const SmemLayout lay_rec = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, 0); /* record offsets */
 
     int rc; /* the window tables were uploaded by the caller before the first chunk */
@@ -440,28 +428,37 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         p.pre_stride = (lay_rec.lpc_stride + 15u) & ~15u;
         if ((rc = sl.pre.ensure(n_sub * (u64)p.pre_stride))) return rc;
         p.pre = (uint8_t *)sl.pre.p;
-        if (split_back) {
-            if ((rc = sl.dec.ensure(n_sub * sizeof(SubDecision)))) return rc;
-            p.dec = (SubDecision *)sl.dec.p;
-        }
+        if ((rc = sl.dec.ensure(n_sub * sizeof(SubDecision)))) return rc;
+        p.dec = (SubDecision *)sl.dec.p;
+    }
+    /* how choose_kernel multiplies: sample pairs against coefficient bytes (16-bit PCM, at most
+     * 8-bit coefficients), 32-bit sums proven exact for every order, or decided per order */
+    int flavour = 2;
+    if (a.bits <= 16 && a.qlp_precision <= 8) flavour = 0;
+    else if (((u64)a.max_lpc_order << (a.qlp_precision - 1 + a.bits - 1)) <= (1ull << 30)) flavour = 1;
+    if (const char *e = getenv("FLACB200_FLAVOUR")) { /* tuning knob: a slower but equally exact flavour */
+        const int v = atoi(e);
+        if (v > flavour && v <= 2) flavour = v;
     }
     auto launch = [&](int kind, int variant, int threads, size_t smem, const EncParams &kp) {
         g_launches++;
-        if (plan.lmax12) return plan.staged ? launch_12_staged(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp)
-                                            : launch_12_fused(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp);
-        return plan.staged ? launch_32_staged(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp)
-                           : launch_32_fused(kind, variant, (unsigned)n_frames, threads, smem, sl.stream, kp);
+        const unsigned grid = (unsigned)n_frames;
+        if (kind == K_FIXED) return launch_fixed(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
+        return plan.lmax12 ? launch_12(kind, variant, flavour, grid, threads, smem, sl.stream, kp)
+                           : launch_32(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
     };
 
     CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 512, sl.stream));
     CUDA_TRY(cudaMemsetAsync(sl.lb.p, 0, n_frames * 8, sl.stream));
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
+    sl.staged = plan.staged;
     if (plan.staged) {
         EncParams pa = p;
         pa.lay = make_layout_front(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.front.threads,
                                    plan.front.all_planes);
         pa.all_planes = plan.front.all_planes;
         CUDA_TRY(launch(K_ANALYSE, plan.front.variant, plan.front.threads, pa.lay.total, pa));
+        CUDA_TRY(cudaEventRecord(sl.ev_s[0], sl.stream));
         const int wpb = 4; /* subframes (warps) per CTA of stage B */
         const size_t smem_b = (size_t)wpb * p.pre_stride;
         EncParams pb = p;
@@ -470,15 +467,15 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         lpc_coefficients_kernel<<<(unsigned)((n_sub + wpb - 1) / wpb), wpb * 32, smem_b, sl.stream>>>(pb, (uint32_t)n_sub);
         CUDA_TRY(cudaGetLastError());
         g_launches++;
-        if (split_back) {
-            EncParams pc = p;
-            pc.lay = make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.choose.threads,
-                                        plan.choose.all_planes);
-            pc.all_planes = plan.choose.all_planes;
-            CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
-        }
+        CUDA_TRY(cudaEventRecord(sl.ev_s[1], sl.stream));
+        EncParams pc = p;
+        pc.lay = make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.choose.threads,
+                                    plan.choose.all_planes);
+        pc.all_planes = plan.choose.all_planes;
+        CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
+        CUDA_TRY(cudaEventRecord(sl.ev_s[2], sl.stream));
     }
-    CUDA_TRY(launch(plan.staged ? (split_back ? K_SERIALISE : K_BACK) : K_FUSED, shape.variant, B, lay.total, p));
+    CUDA_TRY(launch(plan.staged ? K_SERIALISE : K_FIXED, shape.variant, B, lay.total, p));
     if (a.flags & FLACB_SLOT_COMPACT) {
         scan_frame_bytes_kernel<<<1, 256, 0, sl.stream>>>(p.frame_bytes, p.frame_off, p.n_frames);
         CUDA_TRY(cudaGetLastError());
@@ -568,7 +565,7 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         if (want * 2 <= n_frames) chunk_frames = want;
     }
     const u64 n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
-    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f;
+    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f, stage_ms[4] = {0.f, 0.f, 0.f, 0.f};
     u64 host_off = 0; /* bytes produced so far */
     int64_t bad_frame = -1;
     u64 ood = 0, hist[6] = {0, 0, 0, 0, 0, 0};
@@ -592,6 +589,15 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1));
         k_ms += ms;
+        if (sl.staged) {
+            cudaEvent_t ev[5] = {sl.ev_k0, sl.ev_s[0], sl.ev_s[1], sl.ev_s[2], sl.ev_k1};
+            for (int k = 0; k < 4; k++) {
+                CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+                stage_ms[k] += ms;
+            }
+        } else {
+            stage_ms[3] += ms;
+        }
         if (host_in) {
             CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_c0, sl.ev_c1));
             h2d_ms += ms;
@@ -709,6 +715,7 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         stats->bytes_out = host_off;
         stats->first_bad_frame = bad_frame;
         stats->kernel_ms = k_ms;
+        for (int k = 0; k < 4; k++) stats->stage_ms[k] = stage_ms[k];
         stats->h2d_ms = h2d_ms;
         stats->d2h_ms = d2h_ms;
         stats->threads_per_frame = threads;

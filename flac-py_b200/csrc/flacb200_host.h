@@ -133,35 +133,24 @@ inline int pick_threads(int block_size, int e, int maxb)
     return b;
 }
 
-/* Launch shape: how many threads per frame, whether every channel plane stays in shared memory,
- * and how many frames share an SM.  The kernel is latency bound (barriers, serial Levinson
- * recursion), so resident frames per SM come first: up to 3 with the <288, 3> instantiation
- * (72 registers), then threads per frame. */
+/* Launch shape of the serialising kernel: how many threads per frame, whether every channel's
+ * plane stays in shared memory, and how many frames share an SM.  The kernel is latency bound
+ * (barriers between its phases), so resident frames per SM come first: up to 3 with the
+ * <288, 3> instantiation (72 registers), then resident planes (nothing reloaded or recomputed
+ * when the frame is serialised). */
 struct LaunchShape {
     int threads, all_planes, ctas_per_sm, variant; /* variant 0: <576,1>, 1: <288,3> */
 };
 
 template <class LayoutFn>
 inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t smem_optin, size_t smem_per_sm,
-                              LayoutFn layout_total, int lpc = 0)
+                              LayoutFn layout_total)
 {
     LaunchShape best = {0, 0, 0, 0};
-    if (lpc) {
-        /* measured (profiles/): with the LPC analysis in the kernel, two resident frames at 96
-         * registers and every plane in shared memory beat three at 72 registers */
-        const int threads = pick_threads(block_size, e, 288);
-        for (int mode = 2; mode >= 1; mode--) { /* 2: also keep every channel's residual for phase 3 */
-            const size_t dyn = layout_total(threads, mode);
-            if (dyn + static_smem <= smem_optin && 2 * (dyn + static_smem + 1024) <= smem_per_sm && 2 * 96 * threads <= 65536) {
-                best = {threads, mode, 2, 0};
-                return best;
-            }
-        }
-    }
     for (int variant = 1; variant >= 0; variant--) {
         const int maxb = variant ? 288 : 576;
         const int regs = variant ? 72 : 96;
-        for (int all_planes = 2; all_planes >= 0; all_planes--) {
+        for (int all_planes = 1; all_planes >= 0; all_planes--) {
             const int threads = pick_threads(block_size, e, maxb);
             const size_t dyn = layout_total(threads, all_planes);
             if (dyn + static_smem > smem_optin) continue;
@@ -171,7 +160,6 @@ inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t 
             if (variant && ctas > 3) ctas = 3;
             if (!variant && ctas > 2) ctas = 2;
             if (ctas < 1) continue;
-            /* more resident warps first, then resident planes (no reload) */
             const int score = ctas * threads * 4 + all_planes;
             const int best_score = best.ctas_per_sm * best.threads * 4 + best.all_planes;
             if (best.threads == 0 || score > best_score) best = {threads, all_planes, ctas, variant};

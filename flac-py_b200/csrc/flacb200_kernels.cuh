@@ -46,7 +46,7 @@ typedef unsigned long long u64;
 typedef long long i64;
 
 constexpr int E = 8;            /* consecutive samples per thread per tile */
-constexpr int GUARD = 32;       /* zero history in front of every channel plane */
+constexpr int GUARD = 64;       /* zero history in front of every channel plane (a multiple of 16: keeps the swizzle phase) */
 constexpr int TAILPAD = 48;     /* zero samples behind a plane (window reads run past the end) */
 #ifndef FLACB_STG_WORDS
 #define FLACB_STG_WORDS 4096
@@ -84,19 +84,26 @@ constexpr u64 LB_AGG = 1ull << 62;
 constexpr u64 LB_PREFIX = 2ull << 62;
 constexpr u64 LB_VALUE = (1ull << 62) - 1;
 
-/* plane index -> shared memory word: one pad word every 32 keeps the stride-E accesses of a
- * warp on distinct banks */
-__host__ __device__ __forceinline__ uint32_t padidx(uint32_t i) { return i + (i >> 5); }
+/* plane index -> shared memory word.  A thread owns runs of 8 consecutive samples and moves them
+ * with 16-byte accesses; a quarter warp's eight accesses are 8 words apart and would only touch
+ * half of the banks, twice.  Flipping bit 2 in every other group of 32 words (swapping the two
+ * halves of every run there) spreads them over all 32 banks without padding.  Aligned groups of
+ * four words stay contiguous, so x[swz(i) .. swz(i) + 3] is samples i .. i + 3 for i % 4 == 0. */
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 4u); }
 
 struct SmemLayout {
     uint32_t xs, xwords, res, cum, kall, stg, stg_words, fb, pst, red, lpc, lpc_stride, total;
     /* per-channel LPC front end, offsets inside a channel's lpc area */
     uint32_t o_autoc, o_levprod, o_ldc, o_qc, o_qmeta, o_fixed;
-    uint32_t chan_stride; /* bytes between the residual / running-sum / parameter areas of two channels */
-    int xs_all, res_all;
+    uint32_t chan_stride; /* bytes between the running-sum / parameter areas of two channels */
+    int xs_all;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+/* row stride of the per-order coefficient tables: rows are padded to a multiple of 8 so that the
+ * fixed-width filter bodies of lpc_errors can read a whole (zero padded) row */
+__host__ __device__ inline int lpc_row_stride(int L) { return (L + 7) & ~7; }
 
 /* Shared memory plan.  all_planes: every channel plane resident; otherwise one plane that is
  * (re)loaded per channel and phase, which leaves room for more CTAs per SM.  `threads` sizes the
@@ -106,8 +113,8 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
                                                    int all_planes)
 {
     SmemLayout l;
-    l.xwords = padidx((uint32_t)(GUARD + nmax + TAILPAD)) + 1;
-    const uint32_t plane = align16(l.xwords * 4);
+    l.xwords = ((uint32_t)(GUARD + nmax + TAILPAD) + 7u) & ~7u;
+    const uint32_t plane = l.xwords * 4;
     int tile = threads * E < nmax ? threads * E : nmax;
     uint32_t words = ((uint32_t)tile * (uint32_t)(bps + 4) + 31) / 32 + 96; /* + serial header part */
     /* better still: the whole frame (one flush, at the end), up to the cap */
@@ -116,25 +123,20 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     if (words < frame_words) words = frame_words;
     if (words < 512) words = 512;
     if (words > (uint32_t)STG_WORDS) words = (uint32_t)STG_WORDS;
-    /* the window doubles as scratch for the autocorrelation partials: 24 bytes per warp and lag */
-    const uint32_t autoc_words = (uint32_t)((threads + 31) / 32) * (FLACB_MAX_LPC + 1) * 6 + 8;
-    if (L > 0 && words < autoc_words) words = autoc_words;
     l.stg_words = words;
-    /* all_planes: 0 one plane (reloaded per channel), 1 every plane resident, 2 every plane and
-     * every channel's residual / running sums / Rice parameters resident (phase 3 recomputes
-     * nothing) */
+    /* all_planes: every channel's plane, running sums and Rice parameters resident (nothing is
+     * reloaded or recomputed when the frame is serialised); otherwise one of each.  The zig-zag
+     * residual of a channel replaces its samples in the plane (residual_and_cum). */
     l.xs_all = all_planes >= 1;
-    l.res_all = all_planes >= 2;
     uint32_t off = 0;
     l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
-    const uint32_t res_b = align16((padidx((uint32_t)(nmax + TAILPAD)) + 1) * 4);
     const uint32_t cum_b = align16(((uint32_t)nmax / E + 4) * 8);
     const uint32_t kall_b = align16(2u << rmax);
-    l.chan_stride = res_b + cum_b + kall_b;
-    l.res = off;
-    l.cum = off + res_b;
-    l.kall = off + res_b + cum_b;
-    off += l.chan_stride * (l.res_all ? (uint32_t)channels : 1u);
+    l.chan_stride = cum_b + kall_b;
+    l.res = l.xs + GUARD * 4; /* sample i and residual i share a word */
+    l.cum = off;
+    l.kall = off + cum_b;
+    off += l.chan_stride * (l.xs_all ? (uint32_t)channels : 1u);
     l.stg = off; off += align16((words + 4) * 4);
     /* reduction scratch; the packer's per-thread arrays live in the same bytes (never live together) */
     const uint32_t thr = (uint32_t)((threads + 31) / 32 * 32);
@@ -147,8 +149,8 @@ __host__ __device__ inline SmemLayout make_layout(int nmax, int channels, int bp
     uint32_t o = 0;
     l.o_autoc = o; o += align16((uint32_t)(L + 1) * 8);
     l.o_levprod = o; o += align16((uint32_t)(L > 0 ? L : 1) * 8);
-    l.o_ldc = o; o += align16((uint32_t)(L * L) * 8);
-    l.o_qc = o; o += align16((uint32_t)(L * L) * 4);
+    l.o_ldc = o; o += align16((uint32_t)(L * lpc_row_stride(L)) * 8);
+    l.o_qc = o; o += align16((uint32_t)(L * lpc_row_stride(L)) * 4);
     l.o_qmeta = o; o += align16((uint32_t)(L > 0 ? L : 1) * 16 + 16); /* shift, ncoef, stat, abs per order + lev_stat */
     l.o_fixed = o; o += 64;
     l.lpc_stride = o;
@@ -166,8 +168,7 @@ __host__ __device__ inline SmemLayout make_layout_front(int nmax, int channels, 
 {
     SmemLayout l = make_layout(nmax, channels, bps, rmax, L, threads, 0);
     l.xs_all = all_planes >= 1;
-    l.res_all = 0;
-    const uint32_t plane = align16(l.xwords * 4);
+    const uint32_t plane = l.xwords * 4;
     uint32_t off = 0;
     l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
     /* both tapered ends of a Tukey(0.5) window: n/2 + 152 samples at most (autocorrelation()
@@ -194,8 +195,7 @@ __host__ __device__ inline SmemLayout make_layout_choose(int nmax, int channels,
 {
     SmemLayout l = make_layout(nmax, channels, bps, rmax, L, threads, 0);
     l.xs_all = all_planes >= 1;
-    l.res_all = 0;
-    const uint32_t plane = align16(l.xwords * 4);
+    const uint32_t plane = l.xwords * 4;
     uint32_t off = 0;
     l.xs = off; off += l.xs_all ? plane * (uint32_t)channels : plane;
     l.res = l.cum = l.kall = l.stg = off;
@@ -272,6 +272,7 @@ struct Shared {
     u64 qsum[MAX_CAND];
     Decision dec[MAX_CH];
     int chan_status[MAX_CH]; /* first error of each channel, in the reference's evaluation order */
+    int32_t warm[MAX_CH][FLACB_MAX_LPC]; /* warm-up samples (the planes become residuals) */
     int cur_ch;
     uint32_t cand_o[MAX_CAND], cand_magic[MAX_CAND];
     uint32_t sizeA[MAX_CAND], sizeB[MAX_CAND], any5[MAX_CAND];
@@ -330,6 +331,31 @@ __device__ __forceinline__ void set_status(Blk &b, int code)
      * stages (callers run in that order), then over the channels in ascending order */
     int &st = b.sh.chan_status[b.sh.cur_ch];
     if (st == 0) st = code;
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* 16-byte shared-memory moves of a thread's runs: N consecutive words starting at logical index
+ * i (i % 4 == 0, N % 4 == 0) of a swizzled array                                           */
+
+template <int N>
+__device__ __forceinline__ void ld_run(const int32_t *x, uint32_t i, int (&v)[N])
+{
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+        const int4 t = *(const int4 *)(x + swz(i + (uint32_t)k));
+        v[k] = t.x, v[k + 1] = t.y, v[k + 2] = t.z, v[k + 3] = t.w;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void st_run(int32_t *x, uint32_t i, const int (&v)[N])
+{
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+        int4 t;
+        t.x = v[k], t.y = v[k + 1], t.z = v[k + 2], t.w = v[k + 3];
+        *(int4 *)(x + swz(i + (uint32_t)k)) = t;
+    }
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -451,50 +477,66 @@ __device__ __forceinline__ int32_t load_sample(const uint8_t *base, u64 s, int c
 }
 
 /* c_only < 0: all channels into their planes (xs_all); otherwise channel c_only into plane 0.
- * CH: compile-time channel count for the common layouts (0 = any, divides at run time). */
+ * CH: compile-time channel count for the common layouts (0 = any, divides at run time).
+ * Plain arguments, no block state: the dispatcher below is out of line (one copy per kernel
+ * instead of one per call site and channel count: 85 KB of code in the first staged build). */
 template <int CH>
-__device__ void load_planes_t(Blk &b, int c_only)
+__device__ __forceinline__ void load_planes_t(const uint8_t *base, int32_t *xs, uint32_t xwords, int n, int channels,
+                                              int cbytes, int c_only, int tid, int B)
 {
-    const EncParams &p = b.p;
-    const int ch = CH ? CH : p.channels;
-    const uint8_t *base = p.pcm + (u64)b.sh.frame * (u64)p.block_size * (u64)ch * (u64)p.cbytes;
-    const bool aligned = (((uintptr_t)base) & (uintptr_t)(p.cbytes - 1)) == 0 || p.cbytes == 3 ||
-                         p.cbytes == 1;
+    const int ch = CH ? CH : channels;
+    const bool aligned = (((uintptr_t)base) & (uintptr_t)(cbytes - 1)) == 0 || cbytes == 3 || cbytes == 1;
     const int planes = c_only < 0 ? ch : 1;
     /* zero guard and tail pad */
-    for (int idx = b.tid; idx < planes * (GUARD + TAILPAD); idx += b.B) {
+    for (int idx = tid; idx < planes * (GUARD + TAILPAD); idx += B) {
         int pl = idx / (GUARD + TAILPAD);
         int j = idx - pl * (GUARD + TAILPAD);
-        int i = j < GUARD ? j : b.n + j; /* logical index GUARD + n + (j - GUARD) */
-        b.xs[(uint32_t)pl * b.xwords + padidx((uint32_t)i)] = 0;
+        int i = j < GUARD ? j : n + j; /* logical index GUARD + n + (j - GUARD) */
+        xs[(uint32_t)pl * xwords + swz((uint32_t)i)] = 0;
     }
-    const int total = b.n * ch;
+    const int total = n * ch;
     int done = 0; /* samples [0, done) are handled by a vector path, the rest one by one */
     auto put = [&](int sidx, int32_t v) {
         /* sample `sidx` of the interleaved frame -> its plane */
         const int i = sidx / ch, c = sidx - i * ch; /* shifts for the compile-time counts */
-        if (c_only < 0) b.xs[(uint32_t)c * b.xwords + padidx((uint32_t)(GUARD + i))] = v;
-        else if (c == c_only) b.xs[padidx((uint32_t)(GUARD + i))] = v;
+        if (c_only < 0) xs[(uint32_t)c * xwords + swz((uint32_t)(GUARD + i))] = v;
+        else if (c == c_only) xs[swz((uint32_t)(GUARD + i))] = v;
     };
-    if (p.cbytes == 2 && (((uintptr_t)base) & 15) == 0) {
-        /* 16-bit: eight samples per 16-byte load */
+    if (cbytes == 2 && (((uintptr_t)base) & 15) == 0) {
+        /* 16-bit: eight samples per 16-byte load; mono and stereo go to their planes with
+         * 16-byte stores (the four / eight samples of a channel are consecutive) */
         const int groups = total >> 3;
         const uint4 *src = (const uint4 *)base;
-        for (int g = b.tid; g < groups; g += b.B) {
+        for (int g = tid; g < groups; g += B) {
             const uint4 w = src[g];
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            int v[8];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                put(8 * g + 2 * k, (int32_t)(int16_t)(ww[k] & 0xFFFFu));
-                put(8 * g + 2 * k + 1, (int32_t)ww[k] >> 16);
+                v[2 * k] = (int32_t)(int16_t)(ww[k] & 0xFFFFu);
+                v[2 * k + 1] = (int32_t)ww[k] >> 16;
+            }
+            if (CH == 1) {
+                st_run<8>(xs, (uint32_t)(GUARD + 8 * g), v);
+            } else if (CH == 2) {
+                const int ev[4] = {v[0], v[2], v[4], v[6]}, od[4] = {v[1], v[3], v[5], v[7]};
+                if (c_only < 0) {
+                    st_run<4>(xs, (uint32_t)(GUARD + 4 * g), ev);
+                    st_run<4>(xs + xwords, (uint32_t)(GUARD + 4 * g), od);
+                } else {
+                    st_run<4>(xs, (uint32_t)(GUARD + 4 * g), c_only == 0 ? ev : od);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) put(8 * g + k, v[k]);
             }
         }
         done = groups << 3;
-    } else if (p.cbytes == 3 && (((uintptr_t)base) & 3) == 0) {
+    } else if (cbytes == 3 && (((uintptr_t)base) & 3) == 0) {
         /* 24-bit: four samples per three 32-bit loads */
         const int groups = total >> 2;
         const uint32_t *src = (const uint32_t *)base;
-        for (int g = b.tid; g < groups; g += b.B) {
+        for (int g = tid; g < groups; g += B) {
             const uint32_t w0 = src[3 * g], w1 = src[3 * g + 1], w2 = src[3 * g + 2];
             put(4 * g, (int32_t)(w0 << 8) >> 8);
             put(4 * g + 1, (int32_t)(((w0 >> 24) | (w1 << 8)) << 8) >> 8);
@@ -503,18 +545,26 @@ __device__ void load_planes_t(Blk &b, int c_only)
         }
         done = groups << 2;
     }
-    for (int sidx = done + b.tid; sidx < total; sidx += b.B) put(sidx, load_sample(base, (u64)sidx, p.cbytes, p.bps, aligned));
+    for (int sidx = done + tid; sidx < total; sidx += B) put(sidx, load_sample(base, (u64)sidx, cbytes, 0, aligned));
+}
+
+static __device__ __noinline__ void load_planes_impl(const uint8_t *base, int32_t *xs, uint32_t xwords, int n, int channels,
+                                                      int cbytes, int c_only, int tid, int B)
+{
+    switch (channels) {
+    case 1: load_planes_t<1>(base, xs, xwords, n, channels, cbytes, c_only, tid, B); break;
+    case 2: load_planes_t<2>(base, xs, xwords, n, channels, cbytes, c_only, tid, B); break;
+    case 8: load_planes_t<8>(base, xs, xwords, n, channels, cbytes, c_only, tid, B); break;
+    default: load_planes_t<0>(base, xs, xwords, n, channels, cbytes, c_only, tid, B); break;
+    }
     __syncthreads();
 }
 
 __device__ __forceinline__ void load_planes(Blk &b, int c_only)
 {
-    switch (b.p.channels) {
-    case 1: load_planes_t<1>(b, c_only); break;
-    case 2: load_planes_t<2>(b, c_only); break;
-    case 8: load_planes_t<8>(b, c_only); break;
-    default: load_planes_t<0>(b, c_only); break;
-    }
+    const EncParams &p = b.p;
+    const uint8_t *base = p.pcm + (u64)b.sh.frame * (u64)p.block_size * (u64)p.channels * (u64)p.cbytes;
+    load_planes_impl(base, b.xs, b.xwords, b.n, p.channels, p.cbytes, c_only, b.tid, b.B);
 }
 
 /* ------------------------------------------------------------------------------------- */
@@ -537,8 +587,7 @@ static __device__ void fixed_errors(Blk &b, const int32_t *x)
         const int i0 = (tile * b.B + b.tid) * E;
         if (i0 < b.n) {
             int a[E + 4];
-#pragma unroll
-            for (int j = 0; j < E + 4; j++) a[j] = x[padidx((uint32_t)(GUARD + i0 - 4 + j))];
+            ld_run<E + 4>(x, (uint32_t)(GUARD + i0 - 4), a);
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 const int i = i0 + e;
@@ -596,11 +645,10 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
             const int i0 = (tile * b.B + b.tid) * E;
             if (i0 < n && autoc_flat(b, i0, L)) {
                 any = true;
-                int xa[E], xb[E + LGI - 1];
-#pragma unroll
-                for (int e = 0; e < E; e++) xa[e] = x[padidx((uint32_t)(GUARD + i0 + e))];
-#pragma unroll
-                for (int j = 0; j < E + LGI - 1; j++) xb[j] = x[padidx((uint32_t)(GUARD + i0 + lag0 + j))];
+                /* lag0 is 0 (LGI = 13, L <= 12) or a multiple of 8 (LGI = 8): aligned runs */
+                int xa[E], xb[(E + LGI - 1 + 3) & ~3];
+                ld_run<E>(x, (uint32_t)(GUARD + i0), xa);
+                ld_run<(E + LGI - 1 + 3) & ~3>(x, (uint32_t)(GUARD + i0 + lag0), xb);
 #pragma unroll
                 for (int l = 0; l < LGI; l++) {
                     if (lag0 + l <= L) {
@@ -635,7 +683,7 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
     if (stored) {
         for (int t = b.tid; t < count; t += b.B) {
             const int i = t < A ? t : Bq + (t - A);
-            wxs[t + (t >> 3)] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i))], b.win[i]);
+            wxs[t + (t >> 3)] = __dmul_rn((double)x[swz((uint32_t)(GUARD + i))], b.win[i]);
         }
         __syncthreads();
     }
@@ -656,11 +704,11 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                 } else {
 #pragma unroll
                     for (int e = 0; e < E; e++)
-                        wa[e] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
+                        wa[e] = __dmul_rn((double)x[swz((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
 #pragma unroll
                     for (int j = 0; j < E + LG - 1; j++) {
                         const int idx = i0 + lag0 + j;
-                        wb[j] = __dmul_rn((double)x[padidx((uint32_t)(GUARD + idx))], b.win[idx]);
+                        wb[j] = __dmul_rn((double)x[swz((uint32_t)(GUARD + idx))], b.win[idx]);
                     }
                 }
 #pragma unroll
@@ -798,80 +846,170 @@ static __device__ void quantize_order(Blk &b, int m, int precision)
 
 /* ------------------------------------------------------------------------------------- */
 /* encoder.py:387-398: sum |residual| of every LPC order 1..L (prediction_residual,
- * encoder.py:537-548).  History window in registers, coefficients broadcast from shared
- * memory, 32-bit accumulation whenever sum|q| * 2^(bps-1) proves it exact.                 */
+ * encoder.py:537-548).  History window in registers, coefficients from shared memory.
+ * Built for the instruction cache:
+ * the orders run in a rolled loop and share a few fixed-width filter bodies (width = order
+ * rounded up, coefficient rows zero padded), so the hot code is a few KB that every warp runs
+ * L times per tile instead of 100+ KB of straight-line code that every warp runs once.
+ * FLAVOUR 0: 16-bit samples and coefficients of at most 8 bits -> two multiply-adds per
+ *            instruction (dp2a on sample pairs / coefficient bytes), 32-bit sums are exact;
+ * FLAVOUR 1: 32-bit sums proven exact for every order on the host (L * 2^(P-1) * 2^(bps-1) <= 2^30);
+ * FLAVOUR 2: 32-bit or 64-bit sums per order: 32-bit whenever sum|q| * 2^(bps-1) <= 2^30 proves
+ *            them exact.
+ * (The first version unrolled every order: 100+ KB of straight-line code per kernel, and the
+ * instruction cache misses were the largest stall reason of the whole encode.)               */
 
-template <int LMAX>
-__device__ void lpc_errors(Blk &b, const int32_t *x, int L)
+#ifdef FLACB_CPU_SIM
+static inline int __dp2a_lo(int a, int bq, int c)
+{
+    return c + (int)(int16_t)(a & 0xFFFF) * (int)(int8_t)(bq & 0xFF) + (int)(int16_t)((unsigned)a >> 16) * (int)(int8_t)((bq >> 8) & 0xFF);
+}
+static inline int __dp2a_hi(int a, int bq, int c)
+{
+    return c + (int)(int16_t)(a & 0xFFFF) * (int)(int8_t)((bq >> 16) & 0xFF) + (int)(int16_t)((unsigned)a >> 16) * (int)(int8_t)((bq >> 24) & 0xFF);
+}
+#endif
+
+/* sum |x[i] - (pred >> shift)| over the thread's E samples; lo/hi: first / one past the last valid
+ * sample of the run (0 / E for interior runs) */
+template <class ACC>
+__device__ __forceinline__ u64 lpc_abs_sum(const int (&xe)[E], const ACC (&acc)[E], int shift, bool interior, int lo, int hi)
+{
+    u64 tot = 0;
+    if (sizeof(ACC) == 4 && interior) {
+#pragma unroll
+        for (int e = 0; e < E; e += 2) { /* |r| < 2^31 each: pairs fit 32 bits */
+            const int r0 = xe[e] - (int)(acc[e] >> shift);
+            const int r1 = xe[e + 1] - (int)(acc[e + 1] >> shift);
+            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            if (e >= lo && e < hi) {
+                const i64 r = (i64)xe[e] - (i64)(acc[e] >> shift);
+                tot += (u64)(r < 0 ? -r : r);
+            }
+        }
+    }
+    return tot;
+}
+
+/* one order with a filter body of width W (W >= order, coefficient row zero padded to W) */
+template <int LMAX, int W, class ACC>
+__device__ __forceinline__ u64 lpc_body(const int (&h)[LMAX + E], const int32_t *q, int shift, bool interior, int lo, int hi)
+{
+    ACC acc[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < W; j4 += 4) {
+        const int4 c4 = *(const int4 *)(q + j4);
+        const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const ACC cj = (ACC)cc[jj];
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] += (ACC)h[LMAX + e - 1 - (j4 + jj)] * cj;
+        }
+    }
+    int xe[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) xe[e] = h[LMAX + e];
+    return lpc_abs_sum<ACC>(xe, acc, shift, interior, lo, hi);
+}
+
+/* dp2a flavour: pk[k] = (h[k] << 16) | (h[k + 1] & 0xFFFF); a coefficient word holds q[4t..4t+3] as
+ * bytes; pair (q[2t], q[2t+1]) meets samples (x[i-1-2t], x[i-2-2t]) = (h[k+1], h[k]), k = LMAX+e-2-2t */
+template <int LMAX, int W>
+__device__ __forceinline__ u64 lpc_body_dp2a(const int (&pk)[LMAX + E - 1], const int (&xe)[E], const uint32_t *q8, int shift,
+                                             bool interior, int lo, int hi)
+{
+    int acc[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) acc[e] = 0;
+#pragma unroll
+    for (int t4 = 0; t4 < W / 4; t4++) {
+        const int cw = (int)q8[t4];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            acc[e] = __dp2a_lo(pk[LMAX + e - 2 - 4 * t4], cw, acc[e]);
+            acc[e] = __dp2a_hi(pk[LMAX + e - 4 - 4 * t4], cw, acc[e]);
+        }
+    }
+    return lpc_abs_sum<int>(xe, acc, shift, interior, lo, hi);
+}
+
+template <int LMAX, int FLAVOUR>
+__device__ void lpc_errors_rolled(Blk &b, const int32_t *x, int L, const uint32_t *q8)
 {
     Shared &sh = b.sh;
     const int n = b.n;
-    const u64 lim32 = 1ull << 30;
-    u64 lane_tot = 0; /* lane m-1 of every warp keeps the warp's running total of order m */
+    constexpr int WSTEP = LMAX <= 12 ? 4 : 8; /* body widths: multiples of WSTEP */
+    constexpr int Q8W = LMAX / 4;              /* packed coefficient words per order */
+    u64 lane_tot = 0; /* lane (m-1) % 32 of every warp keeps the warp's running total of order m */
     for (int tile = 0; tile < b.ntiles; tile++) {
         const int i0 = (tile * b.B + b.tid) * E;
-        const bool interior = i0 >= LMAX && i0 + E <= n; /* no warm-up or end-of-block masking */
+        const bool interior = i0 >= LMAX && i0 + E <= n;
         int h[LMAX + E];
+        if (i0 < n) {
+            ld_run<LMAX + E>(x, (uint32_t)(GUARD + i0 - LMAX), h);
+        } else {
 #pragma unroll
-        for (int j = 0; j < LMAX + E; j++) h[j] = i0 < n ? x[padidx((uint32_t)(GUARD + i0 - LMAX + j))] : 0;
+            for (int j = 0; j < LMAX + E; j++) h[j] = 0;
+        }
+        int pk[LMAX + E - 1], xe[E];
+        if (FLAVOUR == 0) {
 #pragma unroll
-        for (int m = 1; m <= LMAX; m++) {
-            if (m <= L && b.qncoef[m - 1] != 0) {
-                const int shift = b.qshift[m - 1];
+            for (int k = 0; k < LMAX + E - 1; k++) pk[k] = (int)__byte_perm((uint32_t)h[k + 1], (uint32_t)h[k], 0x5410);
+#pragma unroll
+            for (int e = 0; e < E; e++) xe[e] = h[LMAX + e];
+        }
+        const int hi = n - i0 < E ? (n - i0 < 0 ? 0 : n - i0) : E;
+#pragma unroll 1
+        for (int m = 1; m <= L; m++) {
+            if (b.qncoef[m - 1] == 0) continue; /* block-uniform */
+            const int shift = b.qshift[m - 1];
+            const int lo = m - i0 > 0 ? m - i0 : 0; /* warm-up samples carry no residual */
+            u64 tot = 0;
+            const int wq = (m + WSTEP - 1) / WSTEP;
+            if (FLAVOUR == 0) {
+                const uint32_t *q = q8 + (m - 1) * Q8W;
+                switch (wq) {
+                case 1: tot = lpc_body_dp2a<LMAX, WSTEP>(pk, xe, q, shift, interior, lo, hi); break;
+                case 2: tot = lpc_body_dp2a<LMAX, 2 * WSTEP>(pk, xe, q, shift, interior, lo, hi); break;
+                case 3: tot = lpc_body_dp2a<LMAX, 3 * WSTEP>(pk, xe, q, shift, interior, lo, hi); break;
+                default:
+                    if (LMAX > 12) tot = lpc_body_dp2a<LMAX, LMAX>(pk, xe, q, shift, interior, lo, hi);
+                    break;
+                }
+            } else {
                 const int32_t *q = b.qc + (m - 1) * b.ldL;
-                const bool small = ((u64)b.qabs[m - 1] << (b.p.bps - 1)) <= lim32; /* 32-bit sums are exact */
-                u64 tot = 0;
+                const bool small = FLAVOUR == 1 || ((u64)b.qabs[m - 1] << (b.p.bps - 1)) <= (1ull << 30);
                 if (small) {
-                    int acc[E];
-#pragma unroll
-                    for (int e = 0; e < E; e++) acc[e] = 0;
-#pragma unroll
-                    for (int j = 0; j < m; j++) {
-                        const int cj = q[j];
-#pragma unroll
-                        for (int e = 0; e < E; e++) acc[e] += h[LMAX + e - 1 - j] * cj;
+                    switch (wq) {
+                    case 1: tot = lpc_body<LMAX, WSTEP, int>(h, q, shift, interior, lo, hi); break;
+                    case 2: tot = lpc_body<LMAX, 2 * WSTEP, int>(h, q, shift, interior, lo, hi); break;
+                    case 3: tot = lpc_body<LMAX, 3 * WSTEP, int>(h, q, shift, interior, lo, hi); break;
+                    default:
+                        if (LMAX > 12) tot = lpc_body<LMAX, LMAX, int>(h, q, shift, interior, lo, hi);
+                        break;
                     }
-                    if (interior) {
-                        /* |r| < 2^31 each: pairs fit 32 bits */
-#pragma unroll
-                        for (int e = 0; e < E; e += 2) {
-                            const int r0 = h[LMAX + e] - (acc[e] >> shift);
-                            const int r1 = h[LMAX + e + 1] - (acc[e + 1] >> shift);
-                            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E; e++) {
-                            const int i = i0 + e;
-                            if (i >= m && i < n) {
-                                const int r = h[LMAX + e] - (acc[e] >> shift);
-                                tot += (u64)(uint32_t)(r < 0 ? -r : r);
-                            }
-                        }
-                    }
-                } else {
-                    /* coefficients too large for 32-bit sums (24-bit input, high precisions) */
-                    i64 acc[E];
-#pragma unroll
-                    for (int e = 0; e < E; e++) acc[e] = 0;
-#pragma unroll
-                    for (int j = 0; j < m; j++) {
-                        const i64 cj = q[j];
-#pragma unroll
-                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
-                    }
-#pragma unroll
-                    for (int e = 0; e < E; e++) {
-                        const int i = i0 + e;
-                        if (i >= m && i < n) {
-                            const i64 r = (i64)h[LMAX + e] - (acc[e] >> shift);
-                            tot += (u64)(r < 0 ? -r : r);
-                        }
+                } else if (FLAVOUR == 2) {
+                    switch (wq) {
+                    case 1: tot = lpc_body<LMAX, WSTEP, i64>(h, q, shift, interior, lo, hi); break;
+                    case 2: tot = lpc_body<LMAX, 2 * WSTEP, i64>(h, q, shift, interior, lo, hi); break;
+                    case 3: tot = lpc_body<LMAX, 3 * WSTEP, i64>(h, q, shift, interior, lo, hi); break;
+                    default:
+                        if (LMAX > 12) tot = lpc_body<LMAX, LMAX, i64>(h, q, shift, interior, lo, hi);
+                        break;
                     }
                 }
-                tot = warp_sum_u64(tot);
-                if (b.lane == m - 1) lane_tot += tot;
             }
+            /* a thread's sum is below 2^36: two reductions of 20-bit / 16-bit pieces are exact */
+            const uint32_t p0 = (uint32_t)tot & 0xFFFFFu, p1 = (uint32_t)(tot >> 20);
+            const u64 wt = (u64)__reduce_add_sync(FULL, p0) + ((u64)__reduce_add_sync(FULL, p1) << 20);
+            if (b.lane == ((m - 1) & 31)) lane_tot += wt;
         }
     }
     b.red[b.warp * RED_STRIDE + b.lane] = lane_tot;
@@ -889,33 +1027,36 @@ __device__ void lpc_errors(Blk &b, const int32_t *x, int L)
  * running sum cum[g] = sum of res[0 .. g*E) that the Rice search reads partition sums from */
 
 template <int LMAX>
-__device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
+__device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d, int c)
 {
+    /* In place: residual i takes the word of sample i (b.res == x + GUARD), so a frame needs no
+     * second array.  A run only reads samples at or in front of itself, so the tiles are walked
+     * from the back: when tile k is replaced (after a barrier: every thread holds its inputs in
+     * registers), the samples tile k - 1 still needs lie in front of it.  The warm-up samples,
+     * which the serialiser writes verbatim, are put aside first. */
     const int n = b.n;
-    u64 base = 0;
     bool range_bad = false;
-    for (int tile = 0; tile < b.ntiles; tile++) {
-        const int g = tile * b.B + b.tid;
-        const int i0 = g * E;
-        u64 run = 0;
+    if (b.tid < d.warm && b.tid < FLACB_MAX_LPC) b.sh.warm[c][b.tid] = x[swz((uint32_t)(GUARD + b.tid))];
+    for (int tile = b.ntiles - 1; tile >= 0; tile--) {
+        const int i0 = (tile * b.B + b.tid) * E;
+        int a[E + 4], h[LMAX + E];
         if (i0 < n) {
-            uint32_t u[E];
+            if (d.type == 0) ld_run<E + 4>(x, (uint32_t)(GUARD + i0 - 4), a);
+            else ld_run<LMAX + E>(x, (uint32_t)(GUARD + i0 - LMAX), h);
+        }
+        __syncthreads();
+        if (i0 < n) {
+            int u[E];
             if (d.type == 0) {
-                int a[E + 4];
-#pragma unroll
-                for (int j = 0; j < E + 4; j++) a[j] = x[padidx((uint32_t)(GUARD + i0 - 4 + j))];
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     int r[5];
                     fixed_residuals(a, e, r);
                     const int rr = d.order == 0 ? r[0] : d.order == 1 ? r[1] : d.order == 2 ? r[2]
                                    : d.order == 3 ? r[3] : r[4];
-                    u[e] = ((uint32_t)rr << 1) ^ (uint32_t)(rr >> 31);
+                    u[e] = (int)(((uint32_t)rr << 1) ^ (uint32_t)(rr >> 31));
                 }
             } else {
-                int h[LMAX + E];
-#pragma unroll
-                for (int j = 0; j < LMAX + E; j++) h[j] = x[padidx((uint32_t)(GUARD + i0 - LMAX + j))];
                 i64 acc[E];
 #pragma unroll
                 for (int e = 0; e < E; e++) acc[e] = 0;
@@ -932,16 +1073,26 @@ __device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d)
                     const i64 r = (i64)h[LMAX + e] - (acc[e] >> d.shift);
                     const u64 z = ((u64)r << 1) ^ (u64)(r >> 63);
                     if ((z >> 32) != 0 && i0 + e >= d.warm && i0 + e < n) range_bad = true;
-                    u[e] = (uint32_t)z;
+                    u[e] = (int)(uint32_t)z;
                 }
             }
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const int i = i0 + e;
-                if (i < d.warm || i >= n) u[e] = 0;
-                b.res[padidx((uint32_t)i)] = u[e];
-                run += u[e];
-            }
+            for (int e = 0; e < E; e++)
+                if (i0 + e < d.warm || i0 + e >= n) u[e] = 0;
+            st_run<E>((int32_t *)b.res, (uint32_t)i0, u);
+        }
+    }
+    /* running sums, front to back: every thread adds up its own runs again */
+    u64 base = 0;
+    for (int tile = 0; tile < b.ntiles; tile++) {
+        const int g = tile * b.B + b.tid;
+        const int i0 = g * E;
+        u64 run = 0;
+        if (i0 < n) {
+            int u[E];
+            ld_run<E>((const int32_t *)b.res, (uint32_t)i0, u);
+#pragma unroll
+            for (int e = 0; e < E; e++) run += (uint32_t)u[e];
         }
         u64 total;
         const u64 ex = block_excl_scan_u64(b, run, total);
@@ -963,7 +1114,7 @@ __device__ __forceinline__ u64 cum_at(const Blk &b, int pos)
 {
     const int g = pos / E;
     u64 s = b.cum[g];
-    for (int j = g * E; j < pos; j++) s += b.res[padidx((uint32_t)j)];
+    for (int j = g * E; j < pos; j++) s += b.res[swz((uint32_t)j)];
     return s;
 }
 
@@ -1054,9 +1205,11 @@ static __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
         for (int tile = 0; tile < b.ntiles; tile++) {
             const int i0 = (tile * b.B + b.tid) * E;
             if (i0 < n) {
+                int ui[E];
+                ld_run<E>((const int32_t *)b.res, (uint32_t)i0, ui);
                 uint32_t u[E];
 #pragma unroll
-                for (int e = 0; e < E; e++) u[e] = b.res[padidx((uint32_t)(i0 + e))];
+                for (int e = 0; e < E; e++) u[e] = (uint32_t)ui[e];
                 const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
                 const uint32_t bnd = (p0 + 1) * psz;
                 uint32_t t32 = 0;
@@ -1311,17 +1464,39 @@ static __device__ void pack_residual(Blk &b, const Decision &d)
         const int i0 = (tile * b.B + b.tid) * E;
         uint32_t u[E], k[E], pre[E]; /* pre: number of prefix bits in front of the code */
         uint32_t nbits = 0;
+        int ui[E];
+        if (i0 < n) {
+            ld_run<E>((const int32_t *)b.res, (uint32_t)i0, ui);
+        } else {
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            const int i = i0 + e;
-            u[e] = 0, k[e] = 0, pre[e] = 0;
-            if (i >= d.warm && i < n) {
-                const uint32_t pi = fast_div((uint32_t)i, psz, magic);
-                const uint32_t pstart = pi * psz < (uint32_t)d.warm ? (uint32_t)d.warm : pi * psz;
-                u[e] = b.res[padidx((uint32_t)i)];
-                k[e] = kk[pi];
-                if ((uint32_t)i == pstart) pre[e] = (uint32_t)d.method + (i == d.warm ? 6u : 0u);
-                nbits += pre[e] + (u[e] >> k[e]) + 1u + k[e];
+            for (int e = 0; e < E; e++) ui[e] = 0;
+        }
+        const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
+        if (i0 >= d.warm && i0 + E <= n && (uint32_t)(i0 + E) <= (p0 + 1) * psz) {
+            /* the usual run: inside the block, behind the warm-up, in one partition; only its
+             * first sample can open the partition */
+            const uint32_t k0 = kk[p0];
+            const uint32_t pstart = p0 * psz < (uint32_t)d.warm ? (uint32_t)d.warm : p0 * psz;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                u[e] = (uint32_t)ui[e], k[e] = k0, pre[e] = 0;
+                nbits += (u[e] >> k0) + 1u + k0;
+            }
+            if ((uint32_t)i0 == pstart) pre[0] = (uint32_t)d.method + (i0 == d.warm ? 6u : 0u);
+            nbits += pre[0];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int i = i0 + e;
+                u[e] = 0, k[e] = 0, pre[e] = 0;
+                if (i >= d.warm && i < n) {
+                    const uint32_t pi = fast_div((uint32_t)i, psz, magic);
+                    const uint32_t pstart = pi * psz < (uint32_t)d.warm ? (uint32_t)d.warm : pi * psz;
+                    u[e] = (uint32_t)ui[e];
+                    k[e] = kk[pi];
+                    if ((uint32_t)i == pstart) pre[e] = (uint32_t)d.method + (i == d.warm ? 6u : 0u);
+                    nbits += pre[e] + (u[e] >> k[e]) + 1u + k[e];
+                }
             }
         }
         uint32_t tile_bits;
@@ -1441,9 +1616,9 @@ static __device__ int build_frame_header(const EncParams &p, int bs, u64 number,
 /* ------------------------------------------------------------------------------------- */
 /* the kernel                                                                             */
 
-/* Stage A of a channel: fixed-predictor errors and the autocorrelation (everything the Levinson
- * recursion needs).  Stage B (analyse_back) follows once every channel's recursion has run. */
-template <int LMAX>
+/* Front end of a channel: fixed-predictor errors and, for LPC configurations, the
+ * autocorrelation (everything the Levinson recursion needs). */
+template <int LMAX, bool LPC>
 __device__ void analyse_front(Blk &b, const int32_t *x)
 {
     const EncParams &p = b.p;
@@ -1451,17 +1626,18 @@ __device__ void analyse_front(Blk &b, const int32_t *x)
     FLACB_MARK(b, 0); /* everything before: load, waits */
     fixed_errors(b, x);
     FLACB_MARK(b, 1);
-    if (L > 0) {
+    if constexpr (LPC) {
         const int bad_win = (b.sh.frame == p.n_frames - 1 && p.tail_size != p.block_size) ? p.win_tail_bad : p.win_full_bad;
         if (b.tid == 0) *b.lev_stat = bad_win ? FLACB_E_ZERODIV : 0; /* encoder.py:437 */
-        if (!bad_win) autocorrelation<4, (LMAX <= 12 ? 13 : 11)>(b, x, L);
+        if (!bad_win) autocorrelation<4, (LMAX <= 12 ? 13 : 8)>(b, x, L);
         FLACB_MARK(b, 2);
     }
 }
 
-/* encoder.py:387-404, :135-157: error of every LPC order, best order, fixed-vs-LPC choice */
-template <int LMAX>
-__device__ void analyse_choose(Blk &b, const int32_t *x, int c)
+/* encoder.py:387-404, :135-157: error of every LPC order, best order, fixed-vs-LPC choice.
+ * FLAVOUR < 0: no LPC analysis in this kernel (fixed predictors only, p.L == 0). */
+template <int LMAX, int FLAVOUR>
+__device__ void analyse_choose(Blk &b, const int32_t *x, int c, const uint32_t *q8)
 {
     Shared &sh = b.sh;
     const EncParams &p = b.p;
@@ -1473,7 +1649,7 @@ __device__ void analyse_choose(Blk &b, const int32_t *x, int c)
     if (L > 0) {
         if (*b.lev_stat == 0) {
             FLACB_MARK(b, 4);
-            lpc_errors<LMAX>(b, x, L);
+            if constexpr (FLAVOUR >= 0) lpc_errors_rolled<LMAX, FLAVOUR>(b, x, L, q8);
             FLACB_MARK(b, 5);
             lpc_ok = true;
         } else if (b.tid == 0) set_status(b, *b.lev_stat);
@@ -1544,7 +1720,7 @@ __device__ void analyse_size(Blk &b, const int32_t *x, int c)
     const EncParams &p = b.p;
     Decision &d = sh.dec[c];
     flacb_subframe_info *inf = p.info ? p.info + ((u64)sh.frame * (u64)p.channels + (u64)c) : nullptr;
-    residual_and_cum<LMAX>(b, x, d);
+    residual_and_cum<LMAX>(b, x, d, c);
     FLACB_MARK(b, 7);
     uint32_t res_bits;
     rice_search(b, d, &res_bits);
@@ -1563,13 +1739,6 @@ __device__ void analyse_size(Blk &b, const int32_t *x, int c)
         }
     }
     __syncthreads();
-}
-
-template <int LMAX>
-__device__ __forceinline__ void analyse_back(Blk &b, const int32_t *x, int c)
-{
-    analyse_choose<LMAX>(b, x, c);
-    analyse_size<LMAX>(b, x, c);
 }
 
 /* point the LPC front-end views of the block state at one record (shared memory or HBM) */
@@ -1643,7 +1812,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
     b.fb = (uint32_t *)(smem + lay.fb);
     b.pst = (uint32_t *)(smem + lay.pst);
     b.red = (u64 *)(smem + lay.red);
-    b.ldL = p.L;
+    b.ldL = lpc_row_stride(p.L);
     b.stg_words = lay.stg_words;
     b.wx_bytes = lay.kall - lay.res;
     if (lay.xs_all) load_planes(b, -1);
@@ -1651,7 +1820,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
         if (!lay.xs_all) load_planes(b, c);
         bind_lpc_record(b, p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride, lay, p.L);
         __syncthreads();
-        analyse_front<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
+        analyse_front<LMAX, true>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
     }
 }
 
@@ -1659,7 +1828,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
  * (encoder.py:387-404, :135-157) -> one SubDecision per subframe in HBM.  Same small footprint
  * as stage A plus the subframes' coefficient records; its code is the unrolled all-orders
  * filter and little else, so the instruction cache holds it. */
-template <int LMAX, int TB, int MINB>
+template <int LMAX, int TB, int MINB, int FLAVOUR>
 __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
@@ -1684,13 +1853,36 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
     b.red = (u64 *)(smem + lay.red);
-    b.ldL = p.L;
+    b.ldL = lpc_row_stride(p.L);
     /* the records of this frame's subframes (autocorrelation only for the introspection record) */
     for (int c = 0; c < p.channels; c++) {
         const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
         uint32_t *loc = (uint32_t *)(smem + lay.lpc + (uint32_t)c * lay.lpc_stride);
         for (uint32_t i = (uint32_t)b.tid; i < lay.o_levprod / 4; i += (uint32_t)b.B) loc[i] = rec[i];
         for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.tid; i < lay.lpc_stride / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+    }
+    __syncthreads();
+    /* coefficient rows zero padded to the row stride (the filter bodies have fixed widths); for
+     * the dp2a flavour also packed as bytes, four to a word, in the (unused) Levinson matrix */
+    for (int idx = b.tid; idx < p.channels * p.L * b.ldL; idx += b.B) {
+        const int c = idx / (p.L * b.ldL), r = idx - c * (p.L * b.ldL);
+        const int m1 = r / b.ldL, j = r - m1 * b.ldL;
+        unsigned char *q = smem + lay.lpc + (uint32_t)c * lay.lpc_stride;
+        const int nco = ((const int32_t *)(q + lay.o_qmeta))[(p.L > 0 ? p.L : 1) + m1]; /* qncoef[m1] */
+        if (j >= nco) ((int32_t *)(q + lay.o_qc))[r] = 0;
+    }
+    __syncthreads();
+    if (FLAVOUR == 0) {
+        for (int idx = b.tid; idx < p.channels * p.L * (LMAX / 4); idx += b.B) {
+            const int c = idx / (p.L * (LMAX / 4)), r = idx - c * (p.L * (LMAX / 4));
+            const int m1 = r / (LMAX / 4), t4 = r - m1 * (LMAX / 4);
+            unsigned char *q = smem + lay.lpc + (uint32_t)c * lay.lpc_stride;
+            const int32_t *row = (const int32_t *)(q + lay.o_qc) + m1 * b.ldL;
+            uint32_t w = 0;
+            for (int k = 0; k < 4; k++)
+                if (4 * t4 + k < b.ldL) w |= ((uint32_t)row[4 * t4 + k] & 0xFFu) << (8 * k);
+            ((uint32_t *)(q + lay.o_ldc))[r] = w;
+        }
     }
     if (lay.xs_all) load_planes(b, -1);
     else __syncthreads();
@@ -1699,7 +1891,7 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
         bind_lpc_record(b, smem + lay.lpc + (uint32_t)c * lay.lpc_stride, lay, p.L);
         if (b.tid == 0) sh.cur_ch = c;
         __syncthreads();
-        analyse_choose<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
+        analyse_choose<LMAX, FLAVOUR>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c, (const uint32_t *)b.ldc);
         SubDecision *out = p.dec + ((u64)f * (u64)p.channels + (u64)c);
         const uint32_t *src = (const uint32_t *)&sh.dec[c];
         for (uint32_t i = (uint32_t)b.tid; i < sizeof(Decision) / 4; i += (uint32_t)b.B) ((uint32_t *)&out->d)[i] = src[i];
@@ -1722,7 +1914,7 @@ __global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p
     b.lane = b.tid & 31;
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;
-    b.ldL = p.L;
+    b.ldL = lpc_row_stride(p.L);
     const SmemLayout &lay = p.lay;
     const uint32_t s = blockIdx.x * (uint32_t)b.nwarps + (uint32_t)b.warp;
     if (s >= n_sub) return;
@@ -1738,14 +1930,15 @@ __global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p
 }
 #endif
 
-/* TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
- * <288, 3> (72 registers) where three frames fit an SM.
- * MODE 0: everything in this kernel.  MODE 1: stage C of the staged pipeline -- the LPC front
- * end of every subframe (fixed errors, quantised coefficients of every order) is read from its
- * record in HBM instead of being computed here.  MODE 2: stage C2 -- the choice of every
- * subframe was made by choose_kernel as well; this kernel computes the winner's residual, the
- * Rice partitions and the bytes. */
-template <int LMAX, int TB, int MINB, int MODE>
+/* The serialising kernel: one CTA per frame, winner's residual -> Rice partitions -> final bytes
+ * at the frame's final place in the stream.
+ * CHOSEN = true : stage C2 of the LPC pipeline (analyse_kernel -> lpc_coefficients_kernel ->
+ *                 choose_kernel -> this): the subframes' choices are read from HBM.
+ * CHOSEN = false: fixed predictors only (max_lpc_order == 0): the fixed-predictor errors and the
+ *                 choice are computed here as well; nothing else is launched.
+ * TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
+ * <288, 3> (72 registers) where three frames fit an SM. */
+template <int LMAX, int TB, int MINB, bool CHOSEN>
 __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
@@ -1786,8 +1979,8 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.xs = (int32_t *)(smem + lay.xs);
     b.xwords = lay.xwords;
     auto select_channel = [&](int c) { /* per-channel areas: residual, running sums, Rice parameters, LPC front end */
-        const uint32_t o = lay.res_all ? (uint32_t)c * lay.chan_stride : 0u;
-        b.res = (uint32_t *)(smem + lay.res + o);
+        const uint32_t o = lay.xs_all ? (uint32_t)c * lay.chan_stride : 0u;
+        b.res = (uint32_t *)(smem + lay.res) + (lay.xs_all ? (uint32_t)c * lay.xwords : 0u); /* the plane itself */
         b.cum = (u64 *)(smem + lay.cum + o);
         b.kall = (uint8_t *)(smem + lay.kall + o);
         bind_lpc_record(b, smem + lay.lpc + (uint32_t)c * lay.lpc_stride, lay, p.L);
@@ -1797,17 +1990,15 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.fb = (uint32_t *)(smem + lay.fb);
     b.pst = (uint32_t *)(smem + lay.pst);
     b.red = (u64 *)(smem + lay.red);
-    b.ldL = p.L;
+    b.ldL = lpc_row_stride(p.L);
     b.stg_words = lay.stg_words;
     b.wx_bytes = lay.kall - lay.res;
     if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
 
     /* ---- phase 0 + 1 ---- */
-    /* stage A of every channel, then the Levinson recursions of all channels side by side (one
-     * warp each: the recursion is a long chain of dependent fp64 operations, 10-20 % of the
-     * frame's time when run per channel), all quantisations in parallel, then stage B */
     if (lay.xs_all) load_planes(b, -1);
-    if constexpr (MODE == 2) {
+    if constexpr (CHOSEN) {
+        /* LPC configurations: the choice of every subframe was made by choose_kernel */
         for (uint32_t i = (uint32_t)b.tid; i < (uint32_t)p.channels * (sizeof(Decision) / 4); i += (uint32_t)b.B) {
             const uint32_t c = i / (uint32_t)(sizeof(Decision) / 4), k = i - c * (uint32_t)(sizeof(Decision) / 4);
             ((uint32_t *)&sh.dec[c])[k] = ((const uint32_t *)&p.dec[(u64)f * (u64)p.channels + c].d)[k];
@@ -1820,67 +2011,17 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
             __syncthreads();
             analyse_size<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
         }
-    } else if constexpr (MODE == 1) {
-        /* the records of this frame's subframes: autocorrelation (for the introspection
-         * record), quantised coefficients, per-order meta data, fixed errors */
-        for (int c = 0; c < p.channels; c++) {
-            const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
-            uint32_t *loc = (uint32_t *)(smem + lay.lpc + (uint32_t)c * lay.lpc_stride);
-            for (uint32_t i = (uint32_t)b.tid; i < lay.o_levprod / 4; i += (uint32_t)b.B) loc[i] = rec[i];
-            for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.tid; i < lay.lpc_stride / 4; i += (uint32_t)b.B) loc[i] = rec[i];
-        }
-        __syncthreads();
-        for (int c = 0; c < p.channels; c++) {
-            if (!lay.xs_all && (p.channels > 1 || c == 0)) load_planes(b, c);
-            select_channel(c);
-            __syncthreads();
-            analyse_back<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
-        }
     } else {
-      if (p.L == 0) {
-        /* fixed predictors only: nothing to wait for between the two stages */
+        /* fixed predictors only (p.L == 0): the whole path in this kernel */
         for (int c = 0; c < p.channels; c++) {
             const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
             if (!lay.xs_all) load_planes(b, c);
             select_channel(c);
             __syncthreads();
-            analyse_front<LMAX>(b, x);
-            analyse_back<LMAX>(b, x, c);
+            analyse_front<LMAX, false>(b, x);
+            analyse_choose<LMAX, -1>(b, x, c, nullptr);
+            analyse_size<LMAX>(b, x, c);
         }
-    } else {
-        for (int c = 0; c < p.channels; c++) {
-            if (!lay.xs_all) load_planes(b, c);
-            select_channel(c);
-            __syncthreads();
-            analyse_front<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs);
-        }
-        __syncthreads();
-        for (int c = b.warp; c < p.channels; c += b.nwarps) {
-            select_channel(c); /* warp-local view; cur_ch is not used by the recursion */
-            if (*b.lev_stat == 0) levinson(b, p.L);
-        }
-        __syncthreads();
-        FLACB_MARK(b, 3);
-        for (int idx = b.tid; idx < p.channels * p.L; idx += b.B) {
-            const int c = idx / p.L, m = idx - c * p.L + 1;
-            select_channel(c);
-            if (*b.lev_stat == 0) quantize_order(b, m, p.P);
-        }
-        __syncthreads();
-        if (b.tid < p.channels) { /* first failing order of each channel (encoder.py:378 runs them in order) */
-            select_channel(b.tid);
-            int st = *b.lev_stat;
-            for (int m = 0; m < p.L && st == 0; m++) st = b.qstat[m];
-            *b.lev_stat = st;
-        }
-        __syncthreads();
-        for (int c = 0; c < p.channels; c++) {
-            if (!lay.xs_all && p.channels > 1) load_planes(b, c);
-            select_channel(c);
-            __syncthreads();
-            analyse_back<LMAX>(b, lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs, c);
-        }
-      }
     }
     if (b.tid == 0) { /* the frame's status: first failing channel */
         for (int c = p.channels - 1; c >= 0; c--)
@@ -1917,10 +2058,10 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         const Decision &d = sh.dec[c];
         const int32_t *x = lay.xs_all ? b.xs + (uint32_t)c * b.xwords : b.xs;
         select_channel(c);
-        if (!lay.res_all) {
+        if (!lay.xs_all) {
             /* only one channel's residual fits: recompute it and the chosen order's parameters */
             if (!lay.xs_all) load_planes(b, c);
-            residual_and_cum<LMAX>(b, x, d);
+            residual_and_cum<LMAX>(b, x, d, c);
             const int psz = b.n >> d.porder;
             for (int pi = b.tid; pi < (1 << d.porder); pi += b.B) {
                 const int start = pi * psz < d.warm ? d.warm : pi * psz;
@@ -1941,7 +2082,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
         if (b.tid == 0) {
             const uint32_t mask = p.bps >= 32 ? 0xFFFFFFFFu : ((1u << p.bps) - 1u);
             put_serial(b, d.type ? (0x20u | (uint32_t)(d.order - 1)) << 1 : (0x08u | (uint32_t)d.order) << 1, 8); /* encoder.py:553-569 */
-            for (int i = 0; i < d.warm; i++) put_serial(b, (uint32_t)x[padidx((uint32_t)(GUARD + i))] & mask, p.bps);
+            for (int i = 0; i < d.warm; i++) put_serial(b, (uint32_t)sh.warm[c][i] & mask, p.bps);
             if (d.type) { /* encoder.py:619-625 */
                 put_serial(b, (uint32_t)(p.P - 1) & 15u, 4);
                 put_serial(b, (uint32_t)d.shift & 31u, 5);

@@ -1,7 +1,7 @@
 /*
- * flacb200_tu.cuh -- body of the four kernel translation units: instantiates the encode kernels
- * for FLACB_TU_LMAX (unroll depth of the LPC loops) and FLACB_TU_STAGED (0: the one-kernel path,
- * 1: the staged pipeline) and defines their launchers (flacb200_launch.h).
+ * flacb200_tu.cuh -- body of the kernel translation units: instantiates the encode kernels for
+ * FLACB_TU_LMAX (unroll depth of the LPC loops; 0: the fixed-predictor kernel) and defines their
+ * launchers (flacb200_launch.h).
  */
 #define FLACB_TU_KERNELS_ONLY 1
 #include "flacb200_launch.h"
@@ -10,10 +10,10 @@ namespace flacb {
 
 #define FLACB_CAT_(a, b) a##b
 #define FLACB_CAT(a, b) FLACB_CAT_(a, b)
-#if FLACB_TU_STAGED
-#define FLACB_TU_NAME FLACB_CAT(FLACB_TU_LMAX, _staged)
+#if FLACB_TU_LMAX
+#define FLACB_TU_NAME FLACB_TU_LMAX
 #else
-#define FLACB_TU_NAME FLACB_CAT(FLACB_TU_LMAX, _fused)
+#define FLACB_TU_NAME fixed
 #endif
 
 template <class K>
@@ -25,30 +25,37 @@ static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem,
     return cudaGetLastError();
 }
 
-cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, unsigned grid, int threads, size_t smem,
+cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour, unsigned grid, int threads, size_t smem,
                                                cudaStream_t stream, const EncParams &p)
 {
+    (void)flavour;
+#if FLACB_TU_LMAX
     constexpr int LM = FLACB_TU_LMAX;
-#if FLACB_TU_STAGED
     switch (kind) {
     case K_ANALYSE:
         return variant ? launch_one(analyse_kernel<LM, 288, 3>, grid, threads, smem, stream, p)
                        : launch_one(analyse_kernel<LM, 576, 1>, grid, threads, smem, stream, p);
     case K_CHOOSE:
-        return variant ? launch_one(choose_kernel<LM, 288, 3>, grid, threads, smem, stream, p)
-                       : launch_one(choose_kernel<LM, 576, 1>, grid, threads, smem, stream, p);
+        switch (flavour) {
+        case 0:
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 0>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 0>, grid, threads, smem, stream, p);
+        case 1:
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 1>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 1>, grid, threads, smem, stream, p);
+        default:
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 2>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 2>, grid, threads, smem, stream, p);
+        }
     case K_SERIALISE:
-        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 2>, grid, threads, smem, stream, p)
-                       : launch_one(encode_frames_kernel<LM, 576, 1, 2>, grid, threads, smem, stream, p);
-    case K_BACK:
-        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 1>, grid, threads, smem, stream, p)
-                       : launch_one(encode_frames_kernel<LM, 576, 1, 1>, grid, threads, smem, stream, p);
+        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, true>, grid, threads, smem, stream, p)
+                       : launch_one(encode_frames_kernel<LM, 576, 1, true>, grid, threads, smem, stream, p);
     default: return cudaErrorInvalidValue;
     }
 #else
-    if (kind != K_FUSED) return cudaErrorInvalidValue;
-    return variant ? launch_one(encode_frames_kernel<LM, 288, 3, 0>, grid, threads, smem, stream, p)
-                   : launch_one(encode_frames_kernel<LM, 576, 1, 0>, grid, threads, smem, stream, p);
+    if (kind != K_FIXED) return cudaErrorInvalidValue;
+    return variant ? launch_one(encode_frames_kernel<12, 288, 3, false>, grid, threads, smem, stream, p)
+                   : launch_one(encode_frames_kernel<12, 576, 1, false>, grid, threads, smem, stream, p);
 #endif
 }
 
@@ -64,10 +71,10 @@ cudaError_t FLACB_CAT(init_, FLACB_TU_NAME)(const uint16_t *crc_tab, const uint1
 size_t FLACB_CAT(static_smem_, FLACB_TU_NAME)()
 {
     cudaFuncAttributes fa;
-#if FLACB_TU_STAGED
-    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, 2>) != cudaSuccess) return 8192;
+#if FLACB_TU_LMAX
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, true>) != cudaSuccess) return 8192;
 #else
-    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, 0>) != cudaSuccess) return 8192;
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1, false>) != cudaSuccess) return 8192;
 #endif
     return fa.sharedSizeBytes;
 }

@@ -23,7 +23,6 @@ OUTPUT_ON_DEVICE = 0x04
 LENIENT = 0x08
 SLOT_COMPACT = 0x10
 PCM_INT32 = 0x20
-FUSED = 0x40  # the whole LPC encode in one kernel per frame instead of the staged pipeline (same bytes)
 
 MAX_LPC = 32
 INFO_PARAMS = 64
@@ -48,7 +47,7 @@ class Stats(C.Structure):
         ("subframes_lpc", C.c_uint64), ("out_of_domain", C.c_uint64), ("bytes_in", C.c_uint64),
         ("bytes_out", C.c_uint64), ("first_bad_frame", C.c_int64), ("kernel_ms", C.c_float),
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("threads_per_frame", C.c_int32),
-        ("smem_bytes", C.c_int32),
+        ("smem_bytes", C.c_int32), ("stage_ms", C.c_float * 4),
     ]
 
 

@@ -54,9 +54,6 @@ enum {
                                        wins ties.  Frames concerned are counted in the stats.     */
 #define FLACB_SLOT_COMPACT    0x10u /* debugging: per-frame worst-case slots + compaction kernel
                                        instead of the single-pass look-back placement            */
-#define FLACB_FUSED           0x40u /* debugging / comparison: the whole LPC encode in one kernel
-                                       per frame instead of the staged pipeline (analysis ->
-                                       coefficients -> choice + serialisation); same bytes       */
 #define FLACB_PCM_INT32       0x20u /* samples are int32 containers (whatever `bits` is); default
                                        is the WAV payload layout, ceil(bits/8) LE bytes/sample    */
 
@@ -75,8 +72,11 @@ typedef struct {
     int64_t  first_bad_frame;   /* frame index (relative to the call) of the status, or -1   */
     float    kernel_ms;         /* CUDA-event time of the kernels of the call                */
     float    h2d_ms, d2h_ms;    /* copy time when host buffers are used (0 otherwise)        */
-    int32_t  threads_per_frame; /* launch shape actually used                                */
+    int32_t  threads_per_frame; /* launch shape actually used (serialising kernel)           */
     int32_t  smem_bytes;
+    float    stage_ms[4];       /* CUDA-event time of the stages of an LPC encode: analysis,
+                                   coefficients, order choice, serialisation (fixed predictors
+                                   only: everything under [3])                               */
 } flacb_stats;
 
 /* Per-subframe introspection (stage-level parity tests; optional, small inputs only). */

@@ -31,6 +31,7 @@
 struct sim_dim3 { unsigned x, y, z; };
 struct double2 { double x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
 
 namespace sim {

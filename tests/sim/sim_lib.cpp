@@ -65,16 +65,18 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
     window_flat_range(wf, block_size, p.flat_full_lo, p.flat_full_hi);
     window_flat_range(wt, p.tail_size, p.flat_tail_lo, p.flat_tail_hi);
 
-    /* plane_mode: 0 = the library's own choice of shape; 1 = one plane, reloaded per channel; 2 = every plane resident */
+    /* plane_mode bits 0-7: 0 = the library's own choice of shape; 1 = one plane, reloaded per channel;
+     * 2 = every plane resident.  Bits 9-10: a slower, equally exact flavour of the all-orders filter. */
     auto layout_total = [&](int threads, int all_planes) {
-        return (size_t)make_layout(block_size, channels, bits, rice_max, max_lpc_order, threads, all_planes).total;
+        return (size_t)make_layout(block_size, channels, bits, rice_max, 0, threads, all_planes).total;
     };
-    LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total, max_lpc_order > 0);
+    LaunchShape shape = pick_shape(block_size, E, 4096, 227 * 1024, 228 * 1024, layout_total);
     if (shape.threads == 0) return FLACB_E_UNSUPPORTED;
     if ((plane_mode & 0xFFu) == 1) shape.all_planes = 0;
     if ((plane_mode & 0xFFu) == 2) shape.all_planes = 1;
     const int B = threads_override ? threads_override : shape.threads;
-    const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, shape.all_planes);
+    const SmemLayout lay = make_layout(block_size, channels, bits, rice_max, 0, B, shape.all_planes);
+    const SmemLayout lay_rec = make_layout(block_size, channels, bits, rice_max, max_lpc_order, B, 0);
     p.all_planes = shape.all_planes;
     p.lay = lay;
 
@@ -102,14 +104,12 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         p.out = out;
         p.out_cap = out_cap;
     }
-    const bool staged = max_lpc_order > 0 && !(flags & FLACB_FUSED);
-    /* bit 8 of plane_mode: choice and serialisation in one kernel (encode_frames_kernel<.., 1>) */
-    const bool split_back = staged && !(plane_mode & 0x100u);
+    const bool staged = max_lpc_order > 0;
     std::vector<uint8_t> pre;
     std::vector<SubDecision> dec;
     if (staged) {
-        /* stages A, B (and C1) of the staged pipeline, same sequence as flacb200.cu */
-        p.pre_stride = (lay.lpc_stride + 15u) & ~15u;
+        /* stages A, B and C1 of the LPC pipeline, same sequence as flacb200.cu */
+        p.pre_stride = (lay_rec.lpc_stride + 15u) & ~15u;
         const uint64_t n_sub = n_frames * (uint64_t)channels;
         pre.assign(n_sub * p.pre_stride, 0xA5);
         p.pre = pre.data();
@@ -125,41 +125,41 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         }
         const int wpb = 4;
         const unsigned nb = (unsigned)((n_sub + wpb - 1) / wpb);
+        EncParams pb = p;
+        pb.lay = lay_rec;
         for (unsigned blk = 0; blk < nb; blk++)
-            sim::run_block(blk, nb, wpb * 32, (size_t)wpb * p.pre_stride, [&]() { lpc_coefficients_kernel(p, (uint32_t)n_sub); });
-        if (split_back) {
-            dec.resize(n_sub);
-            memset(dec.data(), 0xA5, n_sub * sizeof(SubDecision));
-            p.dec = dec.data();
-            EncParams pc = p;
-            pc.lay = make_layout_choose(block_size, channels, bits, rice_max, max_lpc_order, B, front_planes);
-            pc.all_planes = front_planes;
-            for (uint64_t f = 0; f < n_frames; f++) {
-                if (max_lpc_order <= 12)
-                    sim::run_block((unsigned)f, (unsigned)n_frames, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1>(pc); });
-                else
-                    sim::run_block((unsigned)f, (unsigned)n_frames, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1>(pc); });
+            sim::run_block(blk, nb, wpb * 32, (size_t)wpb * p.pre_stride, [&]() { lpc_coefficients_kernel(pb, (uint32_t)n_sub); });
+        dec.resize(n_sub);
+        memset(dec.data(), 0xA5, n_sub * sizeof(SubDecision));
+        p.dec = dec.data();
+        EncParams pc = p;
+        pc.lay = make_layout_choose(block_size, channels, bits, rice_max, max_lpc_order, B, front_planes);
+        pc.all_planes = front_planes;
+        int flavour = 2;
+        if (bits <= 16 && qlp_precision <= 8) flavour = 0;
+        else if (((u64)max_lpc_order << (qlp_precision - 1 + bits - 1)) <= (1ull << 30)) flavour = 1;
+        if ((int)((plane_mode >> 9) & 3u) > flavour) flavour = (int)((plane_mode >> 9) & 3u);
+        for (uint64_t f = 0; f < n_frames; f++) {
+            const unsigned fu = (unsigned)f, g = (unsigned)n_frames;
+            if (max_lpc_order <= 12) {
+                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 0>(pc); });
+                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 1>(pc); });
+                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 2>(pc); });
+            } else {
+                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 0>(pc); });
+                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 1>(pc); });
+                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 2>(pc); });
             }
-            /* stage C2 carries no LPC front end in shared memory */
-            p.lay = make_layout(block_size, channels, bits, rice_max, 0, B, shape.all_planes);
         }
     }
     const size_t dyn = p.lay.total;
     for (uint64_t f = 0; f < n_frames; f++) {
-        if (split_back) {
-            if (max_lpc_order <= 12)
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 2>(p); });
-            else
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 2>(p); });
-        } else if (staged) {
-            if (max_lpc_order <= 12)
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 1>(p); });
-            else
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 1>(p); });
-        } else if (max_lpc_order <= 12)
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, 0>(p); });
+        if (!staged)
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, false>(p); });
+        else if (max_lpc_order <= 12)
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, true>(p); });
         else
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, 0>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, true>(p); });
     }
     if (flags & FLACB_SLOT_COMPACT) {
         sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(frame_bytes.data(), frame_off.data(), (uint32_t)n_frames); });

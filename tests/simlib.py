@@ -23,7 +23,6 @@ FLAG_SPEC_CHANNELS = 0x01
 FLAG_LENIENT = 0x08
 FLAG_SLOT_COMPACT = 0x10
 FLAG_PCM_INT32 = 0x20
-FLAG_FUSED = 0x40
 
 
 class Stats(C.Structure):
@@ -32,7 +31,7 @@ class Stats(C.Structure):
         ("subframes_lpc", C.c_uint64), ("out_of_domain", C.c_uint64), ("bytes_in", C.c_uint64),
         ("bytes_out", C.c_uint64), ("first_bad_frame", C.c_int64), ("kernel_ms", C.c_float),
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("threads_per_frame", C.c_int32),
-        ("smem_bytes", C.c_int32),
+        ("smem_bytes", C.c_int32), ("stage_ms", C.c_float * 4),
     ]
 
 
