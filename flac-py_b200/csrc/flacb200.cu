@@ -104,7 +104,7 @@ struct flacb_ctx {
     bool win_full_ok = true, win_tail_ok = true;
     int flat_full[2] = {0, 0}, flat_tail[2] = {0, 0};
     /* decode */
-    DevBuf d_stream, d_pcm, d_cand, d_frames, d_dmisc;
+    DevBuf d_stream, d_pcm, d_cand, d_frames, d_dmisc, d_recs;
     HostBuf h_dmeta;
 };
 
@@ -183,7 +183,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->win_full, &c->win_tail, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames, &c->d_dmisc};
+    DevBuf *bufs[] = {&c->win_full, &c->win_tail, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames, &c->d_dmisc, &c->d_recs};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < FLACB_SLOTS; i++) {
         EncSlot &sl = c->slot[i];
@@ -805,8 +805,16 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
         const int v = atoi(e);
         if (v >= 1 && v <= 32) lanes = v;
     }
-    decode_frames_kernel<<<(unsigned)((n_cand + lanes - 1) / lanes), 32, 0, c->stream>>>(d_s, len, d_cand, (uint32_t)n_cand, d_tmpoff,
-                                                                                         d_tmp, check_crc8, lanes);
+    /* one record per possible subframe of every candidate: what restore_kernel has to do */
+    const u64 n_slots = n_cand * (u64)SUBREC_SLOTS;
+    if ((rc = c->d_recs.ensure(n_slots * sizeof(SubRec)))) return rc;
+    SubRec *d_recs = (SubRec *)c->d_recs.p;
+    CUDA_TRY(cudaMemsetAsync(d_recs, 0, n_slots * sizeof(SubRec), c->stream));
+    const u64 n_warps = (n_cand + (u64)lanes - 1) / (u64)lanes;
+    decode_frames_kernel<<<(unsigned)((n_warps + DECODE_WARPS - 1) / DECODE_WARPS), 32 * DECODE_WARPS, 0, c->stream>>>(
+        d_s, len, d_cand, (uint32_t)n_cand, d_tmpoff, d_tmp, d_recs, check_crc8, lanes);
+    restore_kernel<<<(unsigned)((n_slots + 63) / 64), 64, 0, c->stream>>>(d_recs, (uint32_t)n_cand, d_tmp);
+    g_launches++;
     chain_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (uint32_t)n_cand, len, d_jump, d_reach, d_res);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());

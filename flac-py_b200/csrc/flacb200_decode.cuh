@@ -8,9 +8,11 @@
  *   D1  find_sync_kernel      every byte position that looks like a frame sync (0xFF 0xF8/0xF9,
  *                             decoder.py:136-138) becomes a candidate, kept in stream order
  *   D2  parse_headers_kernel  one thread per candidate: frame header fields (decoder.py:133-262)
- *   D3  decode_frames_kernel  one thread per candidate: subframes, Rice residuals and the serial
- *                             prediction restore (decoder.py:267-421, :453-498), into a planar
- *                             scratch area; records where the frame ends
+ *   D3  decode_frames_kernel  one thread per candidate: subframe headers, warm-up samples and
+ *                             Rice residuals (decoder.py:267-421) into a planar scratch area;
+ *                             records where the frame ends and what every subframe needs for
+ *       restore_kernel        the serial prediction restore (decoder.py:453-498): one thread per
+ *                             subframe, history and coefficients in registers
  *   D4  chain_kernel          which candidates are real: the frames the reference would visit
  *                             are exactly the chain "frame 0, then the candidate that starts
  *                             where the previous one ended"; found by pointer jumping.  False
@@ -61,6 +63,16 @@ struct DecodeResult {
     int32_t status, frame_channels;
     u64 bad_frame;
 };
+
+/* what restore_kernel needs to know about one subframe (slot candidate * 8 + channel) */
+struct SubRec {
+    u64 off;        /* first sample of the subframe in the planar scratch area */
+    int32_t bs;
+    int32_t kind;   /* 0: nothing to restore (constant, verbatim, not decoded), 1: fixed, 2: LPC */
+    int32_t order, shift;
+    int32_t coef[FLACB_MAX_LPC];
+};
+constexpr int SUBREC_SLOTS = 8; /* subframes per candidate */
 
 #ifndef FLACB_HOST_ONLY
 
@@ -305,20 +317,6 @@ __global__ void parse_headers_kernel(const uint8_t *s, u64 len, int si_bits, Can
  * in ST_RICE (one Rice code per step, at most one refill per step), so the warp stays
  * converged; header fields, warm-up samples, partition parameters are rare steps. */
 
-/* Last 32 reconstructed samples, circular (LPC subframes).  Kept as int32: the samples of a valid
- * stream fit (the decoder's output is int32 anyway), and for the garbage "frames" behind false
- * sync candidates any value will do. */
-struct History {
-    int32_t h[32];
-    int head;
-    __device__ __forceinline__ void push(int32_t v)
-    {
-        h[head & 31] = v;
-        head++;
-    }
-    __device__ __forceinline__ int32_t back(int j) const { return h[(head - 1 - j) & 31]; } /* x[i-1-j] */
-};
-
 enum {
     ST_SUB_HDR = 0, /* subframe header byte, wasted bits (decoder.py:318-355) */
     ST_WASTED,      /* unary wasted-bits count in progress */
@@ -343,7 +341,6 @@ struct LaneState {
     int pos, idx;                         /* sample position in the subframe; warm-up / coef index */
     int method, porder, parts_left, part_left, k, esc_size;
     u64 cnt;                              /* zeros of an unfinished unary run */
-    int32_t x1, x2, x3, x4;               /* last four samples (fixed predictors, common.py:15-21) */
     int32_t *out;                         /* this channel's plane in the scratch area */
 };
 
@@ -375,29 +372,15 @@ __device__ __forceinline__ void lane_refill(BitReader &g)
     }
 }
 
-__device__ __forceinline__ void lane_store(LaneState &st, History &hist, const int32_t *coef, i64 r)
+__device__ __forceinline__ void lane_store(LaneState &st, i64 r)
 {
-    /* prediction restore of decoder.py:493-498 on the fly.  Sums of the fixed predictors wrap
-     * modulo 2^32, which leaves the stored low 32 bits exact; the LPC sum needs 64 bits because
-     * of the shift. */
-    int32_t v;
-    if (st.type <= 12) {
-        const int o = st.order;
-        const int32_t pred = o == 0 ? 0 : o == 1 ? st.x1 : o == 2 ? 2 * st.x1 - st.x2
-                             : o == 3 ? 3 * st.x1 - 3 * st.x2 + st.x3 : 4 * st.x1 - 6 * st.x2 + 4 * st.x3 - st.x4;
-        v = (int32_t)((uint32_t)r + (uint32_t)pred);
-    } else {
-        i64 acc = 0;
-        for (int j = 0; j < st.order; j++) acc += (i64)hist.back(j) * (i64)coef[j];
-        v = (int32_t)(r + (acc >> (st.shift < 0 ? 0 : st.shift)));
-        hist.push(v);
-    }
-    st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = v;
-    st.out[st.pos++] = v;
+    /* the residual only; restore_kernel adds the prediction (decoder.py:493-498).  The low 32 bits
+     * are all it needs: the sums wrap modulo 2^32, which leaves the stored int32 samples exact */
+    st.out[st.pos++] = (int32_t)r;
     if (--st.part_left == 0) st.state = st.parts_left > 0 ? ST_PART_HDR : ST_SUB_HDR + 100; /* 100+: subframe done */
 }
 
-__device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t *coef, int32_t *tmp, u64 tmp_off)
+__device__ __forceinline__ void lane_step(LaneState &st, SubRec *recs, int32_t *tmp, u64 tmp_off)
 {
     BitReader &g = st.g;
     switch (st.state) {
@@ -419,14 +402,14 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
         const u64 lsb = g.read(st.k);
         if (g.eof) return lane_fail(st, FLACB_E_EOF);
         const u64 u = (msb << st.k) | lsb;
-        lane_store(st, hist, coef, (i64)(u >> 1) ^ -(i64)(u & 1)); /* utils.py:87-88 */
+        lane_store(st, (i64)(u >> 1) ^ -(i64)(u & 1)); /* utils.py:87-88 */
         break;
     }
     case ST_ESCAPED: {
         lane_refill(g);
         const i64 r = g.read_signed(st.esc_size);
         if (g.eof) return lane_fail(st, FLACB_E_EOF);
-        lane_store(st, hist, coef, r);
+        lane_store(st, r);
         break;
     }
     case ST_PART_HDR: {
@@ -471,8 +454,6 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
         lane_refill(g);
         const i64 v = g.read_signed(st.ss);
         if (g.eof) return lane_fail(st, FLACB_E_EOF);
-        hist.push((int32_t)v);
-        st.x4 = st.x3, st.x3 = st.x2, st.x2 = st.x1, st.x1 = (int32_t)v;
         st.out[st.idx++] = (int32_t)v;
         st.pos = st.idx;
         break;
@@ -495,7 +476,7 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
             break;
         }
         lane_refill(g);
-        coef[st.idx++] = (int32_t)g.read_signed(st.precision);
+        recs[st.ch < SUBREC_SLOTS ? st.ch : 0].coef[st.idx++] = (int32_t)g.read_signed(st.precision);
         if (g.eof) return lane_fail(st, FLACB_E_EOF);
         break;
     }
@@ -518,8 +499,6 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
         st.ss = st.sample_size + extra;
         st.out = tmp + tmp_off + (u64)st.ch * (u64)st.bs;
         st.pos = 0, st.idx = 0, st.shift = 0, st.cnt = 0;
-        st.x1 = st.x2 = st.x3 = st.x4 = 0;
-        hist.head = 0;
         st.order = st.type >= 32 ? (st.type & 31) + 1 : st.type >= 8 ? (st.type & 7) : 0;
         st.state = wflag ? ST_WASTED : (st.type == 0 ? ST_CONST : st.type == 1 ? ST_VERBATIM : ST_WARMUP);
         break;
@@ -582,23 +561,100 @@ __device__ __forceinline__ void lane_step(LaneState &st, History &hist, int32_t 
     }
     if (st.state == ST_SUB_HDR + 100) { /* subframe complete */
         if (st.type >= 32 && st.shift < 0) return lane_fail(st, FLACB_E_VALUE); /* >> negative, decoder.py:497 */
+        if (st.ch < SUBREC_SLOTS) {
+            SubRec &r = recs[st.ch];
+            r.off = (u64)(st.out - tmp);
+            r.bs = st.bs;
+            r.order = st.order;
+            r.shift = st.shift;
+            r.kind = st.type >= 32 ? 2 : (st.type >= 8 && st.order > 0) ? 1 : 0;
+        }
         st.ch++;
         st.state = ST_SUB_HDR;
     }
 }
 
-/* frames per warp: fewer than 32 trades idle lanes for less divergence between the lanes' states
- * and more warps per SM (the kernel is bound by the latency of one warp's instruction stream) */
-constexpr int DECODE_LANES = 8; /* default; the launch passes the value in use */
+/* The hot loop: Rice codes of the current partition for as long as nothing unusual happens (whole
+ * aligned words left in the stream, no unary run of 32 or more zeros, parameter below 27).  The
+ * bit window is two big-endian 32-bit words and a cursor, fields are cut out with funnel shifts,
+ * the word behind the window is fetched a code or two before it is needed: about 30 32-bit
+ * instructions per code, the same for every lane, so a warp's lanes stay converged here.
+ * Everything else (partition and subframe headers, warm-up, the ends of the stream, escapes,
+ * long zero runs) is a step of the general state machine above. */
+constexpr int RICE_BURST = 32;
 
-__global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
-                                                           const u64 *tmp_off, int32_t *tmp, int filter, int lanes)
+#ifdef FLACB_CPU_SIM
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
 {
-    const uint32_t ci = (int)threadIdx.x < lanes ? blockIdx.x * (uint32_t)lanes + threadIdx.x : n_cand;
+    const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    return (unsigned)((v << (shift & 31)) >> 32);
+}
+#endif
+
+__device__ __forceinline__ void rice_fast(LaneState &st)
+{
+    BitReader &g = st.g;
+    const int k = st.k;
+    if (st.cnt != 0 || k > 26) return;
+    /* absolute bit position -> aligned word and offset inside it */
+    const u64 bitpos = g.next * 8 - (u64)g.avail;
+    const uintptr_t addr = (uintptr_t)g.p + (uintptr_t)(bitpos >> 3);
+    const uint32_t *wp = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const int64_t wbyte = (int64_t)((uintptr_t)wp - (uintptr_t)g.p); /* byte offset of the window in the stream */
+    if (wbyte < 0 || (u64)wbyte + 12 > g.len) return;
+    /* an iteration moves the window by two words at most; three words are read ahead */
+    const u64 words_left = (g.len - (u64)wbyte) / 4;
+    int n = st.part_left < RICE_BURST ? st.part_left : RICE_BURST;
+    if ((u64)n > (words_left - 3) / 2) n = (int)((words_left - 3) / 2);
+    if (n <= 0) return;
+    uint32_t o = (uint32_t)(bitpos - (u64)wbyte * 8);
+    uint32_t w0 = __byte_perm(wp[0], 0, 0x0123), w1 = __byte_perm(wp[1], 0, 0x0123), pre = wp[2];
+    wp += 3;
+    int32_t *out = st.out + st.pos;
+    int done = 0;
+    for (; done < n; done++) {
+        const uint32_t top = __funnelshift_l(w1, w0, o);
+        if (top == 0) break; /* 32 zeros or more: the general path counts them */
+        const uint32_t z = (uint32_t)__clz((int)top);
+        o += z + 1;
+        if (o >= 32) {
+            w0 = w1, w1 = __byte_perm(pre, 0, 0x0123), pre = *wp++;
+            o -= 32;
+        }
+        const uint32_t lsb = (__funnelshift_l(w1, w0, o) >> 1) >> (31 - k);
+        o += (uint32_t)k;
+        if (o >= 32) {
+            w0 = w1, w1 = __byte_perm(pre, 0, 0x0123), pre = *wp++;
+            o -= 32;
+        }
+        const uint32_t u = (z << k) | lsb; /* z < 32, k < 27, and z << k < 2^31 ... fits */
+        out[done] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); /* utils.py:87-88 */
+    }
+    if (done == 0) return;
+    /* back to the reader's form: the window's remaining bits, left aligned; next = the word behind it */
+    g.buf = (((u64)w0 << 32) | (u64)w1) << o;
+    g.avail = 64 - (int)o;
+    g.next = (u64)((uintptr_t)wp - (uintptr_t)g.p) - 4; /* wp is one behind `pre` */
+    g.pre_ok = false;
+    st.pos += done;
+    st.part_left -= done;
+    if (st.part_left == 0) st.state = st.parts_left > 0 ? ST_PART_HDR : ST_SUB_HDR + 100;
+}
+
+/* frames per warp: fewer than 32 trades idle lanes for less divergence between the lanes' states
+ * and more warps per SM (the kernel is bound by the latency of one lane's instruction stream:
+ * refill, count zeros, shift, read k bits, store) */
+constexpr int DECODE_LANES = 8;  /* default; the launch passes the value in use */
+constexpr int DECODE_WARPS = 4;  /* warps per CTA */
+
+__global__ void __launch_bounds__(32 * DECODE_WARPS) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
+                                                                          const u64 *tmp_off, int32_t *tmp, SubRec *recs,
+                                                                          int filter, int lanes)
+{
+    const int lane = (int)threadIdx.x & 31;
+    const uint32_t wid = blockIdx.x * (uint32_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t ci = lane < lanes && (u64)wid * (u64)lanes + (u64)lane < (u64)n_cand ? wid * (uint32_t)lanes + (uint32_t)lane : n_cand;
     LaneState st;
-    History hist;
-    int32_t coef[FLACB_MAX_LPC];
-    hist.head = 0;
     st.state = ST_DONE;
     st.status = FLACB_E_EOF;
     Candidate c;
@@ -623,8 +679,15 @@ __global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64
         }
     }
     const bool active = ci < n_cand && c.status == FLACB_OK;
+    SubRec *my_recs = recs + (u64)(ci < n_cand ? ci : 0) * SUBREC_SLOTS;
     while (__any_sync(0xffffffffu, st.state != ST_DONE)) {
-        if (st.state != ST_DONE) lane_step(st, hist, coef, tmp, my_off);
+        bool general = st.state != ST_DONE;
+        if (st.state == ST_RICE) {
+            const int before = st.part_left;
+            rice_fast(st);
+            general = st.state != ST_RICE || st.part_left == before; /* no progress: the general path takes the code */
+        }
+        if (general) lane_step(st, my_recs, tmp, my_off);
     }
     if (ci < n_cand) {
         if (active) {
@@ -633,6 +696,86 @@ __global__ void __launch_bounds__(32) decode_frames_kernel(const uint8_t *s, u64
         }
         cand[ci] = c;
     }
+}
+
+/* ---- prediction restore (decoder.py:453-498 _decode_prediction) -------------------------- */
+
+/* result[i] += (sum_j result[i-1-j] * c[j]) >> shift, serially: one thread per subframe, the last
+ * W samples and the coefficients in registers (W >= order, coefficients beyond the order are
+ * zero).  The term of the newest sample is added last, so the chain from one sample to the next
+ * is one multiply-add, a shift and an add.  Residuals are read eight at a time, one chunk ahead
+ * of the arithmetic (the plane is rewritten in place, and a load behind a store to the same
+ * line would wait for L2 on every sample). */
+constexpr int RESTORE_CHUNK = 8;
+
+template <int W>
+__device__ __forceinline__ void restore_run(int32_t *x, int bs, int order, int shift, const int (&c)[W])
+{
+    int h[W]; /* h[j] = x[i - 1 - j] */
+#pragma unroll
+    for (int j = 0; j < W; j++) h[j] = j < order ? x[order - 1 - j] : 0;
+    int cur[RESTORE_CHUNK], nxt[RESTORE_CHUNK];
+#pragma unroll
+    for (int e = 0; e < RESTORE_CHUNK; e++) cur[e] = order + e < bs ? x[order + e] : 0;
+    for (int i0 = order; i0 < bs; i0 += RESTORE_CHUNK) {
+#pragma unroll
+        for (int e = 0; e < RESTORE_CHUNK; e++) nxt[e] = i0 + RESTORE_CHUNK + e < bs ? x[i0 + RESTORE_CHUNK + e] : 0;
+#pragma unroll
+        for (int e = 0; e < RESTORE_CHUNK; e++) {
+            i64 a0 = 0, a1 = 0;
+#pragma unroll
+            for (int j = W - 1; j >= 1; j--) {
+                if (j & 1) a1 += (i64)h[j] * (i64)c[j];
+                else a0 += (i64)h[j] * (i64)c[j];
+            }
+            const i64 acc = (a0 + a1) + (i64)h[0] * (i64)c[0];
+            const int32_t v = (int32_t)((i64)cur[e] + (acc >> shift));
+#pragma unroll
+            for (int j = W - 1; j > 0; j--) h[j] = h[j - 1];
+            h[0] = v;
+            cur[e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < RESTORE_CHUNK; e++)
+            if (i0 + e < bs) x[i0 + e] = cur[e];
+#pragma unroll
+        for (int e = 0; e < RESTORE_CHUNK; e++) cur[e] = nxt[e];
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void restore_any(int32_t *x, const SubRec &r)
+{
+    int c[W];
+    int shift = 0;
+    if (r.kind == 1) {
+        /* the fixed predictors are LPC filters with shift 0 (common.py:15-21); their sums wrap
+         * modulo 2^32 like the int32 samples they are stored in */
+        const int tab[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+#pragma unroll
+        for (int j = 0; j < W; j++) c[j] = j < 4 ? tab[r.order][j] : 0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j++) c[j] = j < r.order ? r.coef[j] : 0;
+        shift = r.shift < 0 ? 0 : r.shift;
+    }
+    restore_run<W>(x, r.bs, r.order, shift, c);
+}
+
+/* thread t: channel t / n_cand of candidate t % n_cand, so that a warp's lanes hold subframes of
+ * the same channel of neighbouring candidates: all of them real for the stream's channels, none
+ * for the rest (those warps leave at once) */
+__global__ void __launch_bounds__(64) restore_kernel(const SubRec *recs, uint32_t n_cand, int32_t *tmp)
+{
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (u64)n_cand * SUBREC_SLOTS) return;
+    const uint32_t ch = (uint32_t)(t / n_cand), ci = (uint32_t)(t - (u64)ch * n_cand);
+    const SubRec &r = recs[(u64)ci * SUBREC_SLOTS + ch];
+    if (r.kind == 0) return;
+    int32_t *x = tmp + r.off;
+    if (r.order <= 8) restore_any<8>(x, r);
+    else if (r.order <= 16) restore_any<16>(x, r);
+    else restore_any<32>(x, r);
 }
 
 /* ---- D4 ------------------------------------------------------------------------------ */

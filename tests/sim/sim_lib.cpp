@@ -233,9 +233,15 @@ static int sim_decode_impl(const uint8_t *frames, uint64_t len, int streaminfo_b
         sim::run_block(b, nb, 128, 0, [&]() { parse_headers_kernel(frames, len, streaminfo_bits, cand.data(), (uint32_t)n_cand, sizes.data(), check_crc8); });
     sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(sizes.data(), tmpoff.data(), (uint32_t)n_cand); });
     std::vector<int32_t> tmp(tmpoff[n_cand] + 16);
-    const unsigned nbd = (unsigned)((n_cand + DECODE_LANES - 1) / DECODE_LANES);
+    std::vector<SubRec> recs(n_cand * SUBREC_SLOTS);
+    memset(recs.data(), 0, recs.size() * sizeof(SubRec));
+    const u64 n_warps = (n_cand + DECODE_LANES - 1) / DECODE_LANES;
+    const unsigned nbd = (unsigned)((n_warps + DECODE_WARPS - 1) / DECODE_WARPS);
     for (unsigned b = 0; b < nbd; b++)
-        sim::run_block(b, nbd, 32, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), check_crc8, DECODE_LANES); });
+        sim::run_block(b, nbd, 32 * DECODE_WARPS, 0, [&]() { decode_frames_kernel(frames, len, cand.data(), (uint32_t)n_cand, tmpoff.data(), tmp.data(), recs.data(), check_crc8, DECODE_LANES); });
+    const unsigned nbr = (unsigned)((recs.size() + 63) / 64);
+    for (unsigned b = 0; b < nbr; b++)
+        sim::run_block(b, nbr, 64, 0, [&]() { restore_kernel(recs.data(), (uint32_t)n_cand, tmp.data()); });
     DecodeResult res;
     sim::run_block(0, 1, 1024, 0, [&]() { chain_kernel(cand.data(), (uint32_t)n_cand, len, jump.data(), reach.data(), &res); });
     if (res.status == STATUS_CRC8_MISMATCH || res.status == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH;
