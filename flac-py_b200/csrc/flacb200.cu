@@ -79,7 +79,9 @@ struct HostBuf {
     }
 };
 
+#ifndef FLACB_SLOTS
 #define FLACB_SLOTS 3
+#endif
 
 /* one encode chunk in flight: its stream, events and buffers */
 struct EncSlot {

@@ -724,18 +724,29 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                 }
             }
         }
+        /* warp sum of the LG double-double partials, transposing as it goes: after the first two
+         * exchanges (lanes 16 and 8 apart) a lane holds one lag's sum over four lanes, three
+         * ordinary butterfly steps finish it: 6 exchanges for 4 lags instead of 20 */
+        static_assert(LG == 4, "the transposed warp sum is written for four lags per pass");
+        {
+            const bool b4 = (b.lane & 16) != 0, b3 = (b.lane & 8) != 0;
+            auto xchg = [&](double &ks, double &kc, double ss, double sc, int off) {
+                const double s2 = __shfl_xor_sync(FULL, ss, off);
+                const double c2 = __shfl_xor_sync(FULL, sc, off);
+                dd_add(ks, kc, s2);
+                kc = __dadd_rn(kc, c2);
+            };
+            /* lanes 16 apart: the lower lane keeps lags 0, 1 and takes the partner's, the upper 2, 3 */
+            double k0s = b4 ? s[2] : s[0], k0c = b4 ? c[2] : c[0], k1s = b4 ? s[3] : s[1], k1c = b4 ? c[3] : c[1];
+            xchg(k0s, k0c, b4 ? s[0] : s[2], b4 ? c[0] : c[2], 16);
+            xchg(k1s, k1c, b4 ? s[1] : s[3], b4 ? c[1] : c[3], 16);
+            /* lanes 8 apart: the lower keeps the first of its two lags */
+            double ks = b3 ? k1s : k0s, kc = b3 ? k1c : k0c;
+            xchg(ks, kc, b3 ? k0s : k1s, b3 ? k0c : k1c, 8);
 #pragma unroll
-        for (int l = 0; l < LG; l++) {
-            if (lag0 + l <= L) {
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double s2 = __shfl_xor_sync(FULL, s[l], off);
-                    const double c2 = __shfl_xor_sync(FULL, c[l], off);
-                    dd_add(s[l], c[l], s2);
-                    c[l] = __dadd_rn(c[l], c2);
-                }
-                if (b.lane == 0) part_d[b.warp * (FLACB_MAX_LPC + 1) + lag0 + l] = make_double2(s[l], c[l]);
-            }
+            for (int off = 4; off > 0; off >>= 1) xchg(ks, kc, ks, kc, off);
+            const int lag = lag0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
+            if ((b.lane & 7) == 0 && lag <= L) part_d[b.warp * (FLACB_MAX_LPC + 1) + lag] = make_double2(ks, kc);
         }
     }
     __syncthreads();
@@ -1406,52 +1417,24 @@ __device__ __forceinline__ void flush_window(Blk &b, uint32_t nbytes, uint32_t w
     flush_window_impl(&b.sh, b.stg, b.stg_words, b.tid, b.B, nbytes, wend);
 }
 
-/* thread-local concatenation of this thread's fields; see pack_residual */
-struct Packer {
-    u64 acc;
-    uint32_t w;       /* word the high half of acc belongs to */
-    uint32_t f_w, l_w;
-    uint32_t win_lo, win_hi;
-    uint32_t firstv, lastv;
-    bool own_first, rmw_first;
-    uint32_t *stg;
-
-    __device__ __forceinline__ void out_word(uint32_t wi, uint32_t v)
-    {
-        if (wi == f_w && !own_first) firstv = v;
-        else if (wi == l_w) lastv = v;
-        else if (wi >= win_lo && wi < win_hi) {
-            if (wi == f_w && rmw_first) stg[wi - win_lo] |= v;
-            else stg[wi - win_lo] = v;
-        }
-    }
-    __device__ __forceinline__ void put(uint32_t bp, uint32_t v, int nb)
-    {
-        const uint32_t tw = bp >> 5;
-        if (tw != w) {
-            out_word(w, (uint32_t)(acc >> 32));
-            if (tw == w + 1) acc <<= 32;
-            else {
-                const uint32_t lo = (uint32_t)acc;
-                if (lo) out_word(w + 1, lo);
-                acc = 0;
-            }
-            w = tw;
-        }
-        acc |= (u64)v << (64 - (int)(bp & 31u) - nb);
-    }
-    __device__ __forceinline__ void finish(uint32_t p_end)
-    {
-        out_word(w, (uint32_t)(acc >> 32));
-        if (((p_end - 1u) >> 5) > w) out_word(w + 1, (uint32_t)acc);
-    }
-};
+/* or `nb` bits (nb <= 32) into the staging window at frame bit position bp, MSB first
+ * (binary.py:144-216).  The window is zero before a frame's bits arrive, so fields only ever set
+ * bits: a shared-memory atomic or per touched word, no ownership protocol between the threads
+ * whose codes share a word.  CHECK: only words inside the window [wbase, wbase + words). */
+template <bool CHECK>
+__device__ __forceinline__ void or_bits(uint32_t *stg, uint32_t wbase, uint32_t words, uint32_t bp, uint32_t v, int nb)
+{
+    const uint32_t wi = (bp >> 5) - wbase;
+    const u64 x = (u64)v << (64 - (int)(bp & 31u) - nb);
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    if (!CHECK || wi < words) atomicOr(&stg[wi], hi);
+    if (lo && (!CHECK || wi + 1u < words)) atomicOr(&stg[wi + 1u], lo);
+}
 
 /* encoder.py:765-806 put_residual: method, partition order, then per partition the parameter
- * and one Rice code per sample (u >> k zeros, a one, k low bits).  Every thread packs the codes
- * of its E consecutive samples into registers; the words strictly inside its bit range are
- * plain shared-memory stores, the first word (shared with the previous thread) is handed to the
- * thread that owns it, and each owner ors the pieces of its last word together.  No atomics. */
+ * and one Rice code per sample (u >> k zeros, a one, k low bits).  A block-wide scan of the
+ * threads' bit counts gives every thread the position of its E codes; the zeros cost nothing
+ * (the window is pre-zeroed), the rest is or-ed in. */
 static __device__ void pack_residual(Blk &b, const Decision &d)
 {
     Shared &sh = b.sh;
@@ -1501,26 +1484,15 @@ static __device__ void pack_residual(Blk &b, const Decision &d)
         }
         uint32_t tile_bits;
         const uint32_t ex = block_excl_scan_u32(b, nbits, tile_bits);
-        b.pst[b.tid] = sh.pos + ex;
         if (tile_bits == 0) continue; /* uniform */
         const uint32_t tile_end = sh.pos + tile_bits;
         if ((tile_end >> 5) >= sh.wbase + b.stg_words) flush_window(b, ((sh.pos >> 5) - sh.wbase) * 4u, sh.pos >> 5);
         else __syncthreads();
         const uint32_t p_start = sh.pos + ex;
-        const uint32_t p_end = p_start + nbits;
         for (;;) {
-            Packer pk;
-            pk.stg = b.stg;
-            pk.win_lo = sh.wbase;
-            pk.win_hi = sh.wbase + b.stg_words;
-            pk.acc = 0;
-            pk.w = p_start >> 5;
-            pk.f_w = p_start >> 5;
-            pk.l_w = nbits ? (p_end - 1u) >> 5 : pk.f_w;
-            pk.rmw_first = b.tid == 0;
-            pk.own_first = b.tid == 0 || (nbits != 0 && (p_start & 31u) == 0);
-            pk.firstv = 0;
-            pk.lastv = 0;
+            const uint32_t wbase = sh.wbase;
+            /* uniform: the whole tile lies inside the window, no range checks needed */
+            const bool fits = (sh.pos >> 5) >= wbase && (tile_end >> 5) + 1u < wbase + b.stg_words;
             if (nbits) {
                 uint32_t cur = p_start;
 #pragma unroll
@@ -1529,30 +1501,22 @@ static __device__ void pack_residual(Blk &b, const Decision &d)
                     if (i >= d.warm && i < n) {
                         if (pre[e]) {
                             if (pre[e] > (uint32_t)d.method) {
-                                pk.put(cur, (method_code << 4) | (uint32_t)d.porder, 6); /* encoder.py:766-767 */
+                                const uint32_t hv = (method_code << 4) | (uint32_t)d.porder; /* encoder.py:766-767 */
+                                if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, hv, 6);
+                                else or_bits<true>(b.stg, wbase, b.stg_words, cur, hv, 6);
                                 cur += 6;
                             }
-                            pk.put(cur, k[e], d.method); /* encoder.py:791 */
+                            if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, k[e], d.method); /* encoder.py:791 */
+                            else or_bits<true>(b.stg, wbase, b.stg_words, cur, k[e], d.method);
                             cur += (uint32_t)d.method;
                         }
-                        const uint32_t q = u[e] >> k[e];
-                        cur += q; /* q zeros: the window is pre-zeroed (encoder.py:802) */
-                        pk.put(cur, (1u << k[e]) | (u[e] & ((1u << k[e]) - 1u)), (int)k[e] + 1);
+                        cur += u[e] >> k[e]; /* q zeros: the window is pre-zeroed (encoder.py:802) */
+                        const uint32_t cv = (1u << k[e]) | (u[e] & ((1u << k[e]) - 1u));
+                        if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, cv, (int)k[e] + 1);
+                        else or_bits<true>(b.stg, wbase, b.stg_words, cur, cv, (int)k[e] + 1);
                         cur += k[e] + 1u;
                     }
                 }
-                pk.finish(p_end);
-            }
-            b.fb[b.tid] = pk.firstv;
-            __syncthreads();
-            /* thread 0 also owns the word the tile starts in when earlier bits sit in it */
-            const bool owns_last = (nbits != 0 || (b.tid == 0 && (p_start & 31u) != 0)) &&
-                                   !(pk.l_w == pk.f_w && !pk.own_first);
-            if (owns_last && pk.l_w >= pk.win_lo && pk.l_w < pk.win_hi) {
-                uint32_t v = pk.lastv;
-                for (int t = b.tid + 1; t < b.B && (b.pst[t] >> 5) == pk.l_w; t++) v |= b.fb[t];
-                if (b.tid == 0 && pk.l_w == pk.f_w) b.stg[pk.l_w - pk.win_lo] |= v;
-                else b.stg[pk.l_w - pk.win_lo] = v;
             }
             __syncthreads();
             if ((tile_end >> 5) < sh.wbase + b.stg_words) break;
