@@ -1,27 +1,35 @@
 /*
  * flacb200_kernels.cuh -- device code of the B200 FLAC encode path.
  *
- * One CTA encodes one frame (all channels) from PCM in HBM to final bytes in HBM:
+ * LPC configurations (max_lpc_order > 0) run as four kernels; every stage is one CTA per frame
+ * except the second, the hand-over between them is a small record per subframe in HBM (HBM is
+ * not the bound of this path: the reference's semantics cost hundreds of integer / fp64
+ * operations per sample against three bytes of traffic, so re-reading the PCM per stage is free
+ * and small single-purpose kernels win on occupancy and instruction cache):
  *
- *   phase 0  frame/channel split: interleaved little-endian PCM -> int32 planes in shared
- *            memory                                     (reference flac/encoder.py:87, :102)
- *   phase 1  per channel: fixed-predictor errors, orders 0-4          (encoder.py:331-359)
- *            windowed fp64 autocorrelation, Levinson-Durbin, coefficient quantisation,
- *            integer residual error of every LPC order                (encoder.py:362-548)
- *            fixed-vs-LPC choice                                      (encoder.py:135-157)
- *            Rice partition search on the winner's residual           (encoder.py:632-760)
- *            -> exact size of every subframe in bits
- *   phase 2  frame size -> byte offset of the frame in the output stream by a decoupled
- *            look-back over a device-wide array of frame sizes (single pass, no second
- *            kernel, no compaction copy)
- *   phase 3  frame header + CRC-8 (encoder.py:194-234), subframes (encoder.py:553-627),
- *            Rice codes (encoder.py:765-806) packed MSB first (binary.py:144-216) in a shared
- *            memory window, flushed to HBM; CRC-16 (encoder.py:159-165, crc.py)
+ *   A   analyse_kernel           frame/channel split (reference flac/encoder.py:87, :102),
+ *                                fixed-predictor errors, orders 0-4 (encoder.py:331-359),
+ *                                windowed fp64 autocorrelation (encoder.py:368-371, :443-450)
+ *   B   lpc_coefficients_kernel  Levinson-Durbin and coefficient quantisation of every order
+ *                                (encoder.py:453-534), one warp per subframe
+ *   C1  choose_kernel            integer residual error of every LPC order on every sample
+ *                                (encoder.py:387-398, :537-548), best order, fixed-vs-LPC
+ *                                choice (encoder.py:135-157)
+ *   C2  encode_frames_kernel     winner's residual in place of the samples, Rice partition
+ *                                search (encoder.py:632-760) -> exact size of every subframe;
+ *                                frame size -> byte offset of the frame in the stream by a
+ *                                decoupled look-back over a device-wide array of frame sizes
+ *                                (single pass, no compaction copy); frame header + CRC-8
+ *                                (encoder.py:194-234), subframes (encoder.py:553-627), Rice
+ *                                codes (encoder.py:765-806) placed MSB first
+ *                                (binary.py:144-216) in a shared memory window, flushed to HBM;
+ *                                CRC-16 (encoder.py:159-165, crc.py)
  *
- * Work split inside the CTA: thread t of tile k owns the E consecutive samples
- * [(k*B + t)*E, +E).  Consecutive samples per thread give the LPC kernels a register-resident
- * history window and let each thread concatenate its own Rice codes in registers; only the
- * first and last word of a thread's bit range are shared with a neighbour.
+ * Fixed predictors only (max_lpc_order == 0): encode_frames_kernel<.., false> does everything.
+ *
+ * Work split inside a CTA: thread t of tile k owns the E consecutive samples [(k*B + t)*E, +E),
+ * moved between shared memory and registers with 16-byte accesses (swz).  Consecutive samples
+ * per thread give the filters a register-resident history window.
  *
  * The same source compiles for the CPU SIMT simulator of tests/sim (FLACB_CPU_SIM), which is
  * test infrastructure: it lets the kernel logic be checked against the golden vectors on a
@@ -235,12 +243,12 @@ struct EncParams {
     flacb_subframe_info *info; /* optional, device memory */
     int all_planes;            /* every channel plane resident in shared memory */
     SmemLayout lay;            /* make_layout(...) of this launch, computed once on the host */
-    /* staged pipeline (analyse_kernel -> lpc_coefficients_kernel -> encode_frames_kernel<.., true>):
-     * per subframe one "LPC front end" record in HBM, laid out like the shared-memory one
-     * (lay.o_autoc .. lay.lpc_stride), pre_stride bytes apart */
+    /* LPC pipeline: per subframe one "LPC front end" record in HBM (autocorrelation, Levinson and
+     * quantised coefficients of every order, fixed-predictor errors), laid out by the o_* offsets
+     * of make_layout, pre_stride bytes apart */
     uint8_t *pre;
     uint32_t pre_stride;
-    SubDecision *dec;          /* [n_frames * channels] choices of choose_kernel for encode_frames_kernel<.., 2> */
+    SubDecision *dec;          /* [n_frames * channels] choices of choose_kernel for encode_frames_kernel<.., true> */
 };
 
 #ifndef FLACB_HOST_ONLY

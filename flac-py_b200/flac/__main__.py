@@ -54,7 +54,7 @@ def cmd_decode(path_in: Path, path_out: Path):
 
 
 def cmd_encode(path_in: Path, path_out: Path, block_size: int, max_lpc_order: int,
-               qlp_coeffs_precision: int, rice_partition_order: range):
+               qlp_coeffs_precision: int, rice_partition_order: range, complete_streaminfo: bool = False):
     with wave_open(str(path_in), mode="rb") as f_in, path_out.open("wb") as f_out:
         parameters = EncoderParameters(
             block_size=block_size,
@@ -68,8 +68,17 @@ def cmd_encode(path_in: Path, path_out: Path, block_size: int, max_lpc_order: in
         frames = f_in.getnframes()
         time_start = timer()
         payload = f_in.readframes(frames)
+        lengths = []
         for bs in encode_pcm(sample_rate, sample_size_bytes * 8, channels, payload, parameters, frames=frames):
             f_out.write(bs)
+            lengths.append(len(bs))
+        if complete_streaminfo:
+            # not in the reference: frame sizes and the MD5 of the PCM, which the reference leaves at
+            # zero (encoder.py:75-81), patched into the STREAMINFO block at byte 8 of the stream
+            from .encoder import complete_streaminfo as _complete, stream_prologue
+            block = stream_prologue(sample_rate, sample_size_bytes * 8, channels, frames, parameters)[2]
+            f_out.seek(8)
+            f_out.write(_complete(block, lengths[3:], payload))
         time_end = timer()
         delta = "{0:.6g}".format(time_end - time_start)
         print(f"Encoding completed in {delta} seconds")
@@ -101,6 +110,10 @@ def make_argument_parser():
         "-r", "--rice-partition-order", type=argparse_range, default=DEFAULT_RICE_PARTITION_ORDER,
         metavar="[M,]N",
         help="[min,]max residual partition order (0..15). min defaults to 0 if unspecified.")
+    encode.add_argument(
+        "--complete-streaminfo", action="store_true",
+        help="Extension (not in the reference): write the minimum / maximum frame size and the MD5 of the "
+             "PCM into STREAMINFO instead of the reference's zeros.")
     return parser
 
 
@@ -113,7 +126,7 @@ def main():
         if isinstance(rpo, str):  # argparse does not run `type` on a string default
             rpo = argparse_range(rpo)
         cmd_encode(args.infile, args.outfile, args.block_size, args.max_lpc_order,
-                   args.qlp_coeff_precision, rpo)
+                   args.qlp_coeff_precision, rpo, args.complete_streaminfo)
 
 
 if __name__ == "__main__":

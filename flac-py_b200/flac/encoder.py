@@ -67,6 +67,27 @@ def stream_prologue(sample_rate: int, sample_size: int, channels: int, frames: i
     return [p[:4], p[4:8], p[8:]]
 
 
+def complete_streaminfo(streaminfo: bytes, frame_lengths, pcm_le: Optional[bytes] = None) -> bytes:
+    """STREAMINFO with the fields the reference leaves at zero (encoder.py:75-81): minimum / maximum
+    frame size in bytes (24 bits each, from the frame lengths the encode returns anyway) and, if
+    the interleaved little-endian PCM is given, its MD5 (16 bytes, as the FLAC format defines
+    it).  `streaminfo` is the 34-byte block (the third chunk of `stream_prologue`).  An
+    extension: the reference never writes these, so a stream patched with this differs from the
+    reference's in exactly these 22 bytes."""
+    import hashlib
+    assert len(streaminfo) == 34
+    lens = [int(v) for v in frame_lengths]
+    out = bytearray(streaminfo)
+    if lens:
+        lo, hi = min(lens), max(lens)
+        assert hi < (1 << 24)
+        out[4:7] = lo.to_bytes(3, "big")
+        out[7:10] = hi.to_bytes(3, "big")
+    if pcm_le is not None:
+        out[18:34] = hashlib.md5(pcm_le).digest()
+    return bytes(out)
+
+
 class _Shard:
     """Frames [f0, f1) of one call on one device."""
 

@@ -130,3 +130,18 @@ def test_cli_parser_defaults_match_the_reference():
     assert (a.block_size, a.max_lpc_order, a.qlp_coeff_precision, a.rice_partition_order) == (16384, 32, 7, range(2, 9))
     a = make_argument_parser().parse_args(["decode", "in.flac", "out.wav"])
     assert a.action == "decode"
+
+
+def test_complete_streaminfo_fills_frame_sizes_and_md5():
+    """extension: the fields the reference leaves at zero (encoder.py:75-81)"""
+    import hashlib
+    from flac.encoder import complete_streaminfo
+    import oracle as O
+    block = O.stream_prologue(44100, 2, 16, 1000, 4608)[8:]
+    assert len(block) == 34 and block[4:10] == bytes(6) and block[18:] == bytes(16)
+    pcm = bytes(range(256)) * 4
+    out = complete_streaminfo(block, [14, 9000, 77], pcm)
+    assert out[:4] == block[:4] and out[10:18] == block[10:18]          # block sizes, rate/channels/bits/total untouched
+    assert int.from_bytes(out[4:7], "big") == 14 and int.from_bytes(out[7:10], "big") == 9000
+    assert out[18:] == hashlib.md5(pcm).digest()
+    assert complete_streaminfo(block, []) == block
