@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <string>
 #include <vector>
@@ -80,8 +81,9 @@ struct HostBuf {
 };
 
 #ifndef FLACB_SLOTS
-#define FLACB_SLOTS 3
+#define FLACB_SLOTS 4
 #endif
+#define FLACB_AHEAD 2 /* chunks enqueued behind the one whose output copy is being started */
 
 /* one encode chunk in flight: its stream, events and buffers */
 struct EncSlot {
@@ -97,6 +99,10 @@ struct EncSlot {
 struct flacb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr; /* stream == slot[0].stream */
+    /* every bulk copy of the chunked host path goes through one stream per direction: a stream's
+     * copies are bound to one copy engine, and with the copies on the chunks' own streams a
+     * chunk's input copy queued up behind another chunk's output copy (measured: no overlap) */
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     int smem_optin = 0, sm_count = 0;
     size_t static_smem12 = 0, static_smem32 = 0;
@@ -152,6 +158,8 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_t0, &c->ev_t1, &c->ev_c0, &c->ev_c1};
     for (cudaEvent_t *e : evs) CUDA_TRY(cudaEventCreate(e));
     for (int i = 0; i < FLACB_SLOTS; i++) {
@@ -203,6 +211,8 @@ extern "C" void flacb_destroy(flacb_ctx *c)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     delete c;
 }
 
@@ -267,6 +277,8 @@ extern "C" int flacb_sync(flacb_ctx *c)
     CUDA_TRY(cudaSetDevice(c->device));
     for (int i = 0; i < FLACB_SLOTS; i++) CUDA_TRY(cudaStreamSynchronize(c->slot[i].stream));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->h2d_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
     return FLACB_OK;
 }
 
@@ -557,19 +569,33 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     }
     const bool host_in = !(flags & FLACB_INPUT_ON_DEVICE), host_out = !(flags & FLACB_OUTPUT_ON_DEVICE);
 
-    /* Host buffers on both sides: cut the frame range into chunks and keep three in flight, so
-     * that the H2D copy of one chunk, the kernel of another and the D2H copy of a third overlap.
+    /* Host buffers on both sides: cut the frame range into chunks and keep several in flight, so
+     * that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap.
      * Chunks are whole waves of resident CTAs.  Everything else: one chunk. */
-    u64 chunk_frames = n_frames;
+    std::vector<u64> chunk_f0; /* first frame of every chunk, then n_frames */
+    chunk_f0.push_back(0);
     if (host_in && host_out && !info && !(flags & FLACB_SLOT_COMPACT)) {
         const u64 wave = (u64)c->sm_count * (u64)plan.shape.ctas_per_sm;
         u64 want = (16ull << 20) / (frame_pcm ? frame_pcm : 1);
         if (const char *e = getenv("FLACB200_CHUNK_FRAMES")) want = (u64)atoll(e);
-        want = (want + wave - 1) / wave * wave;
+        want = (want + wave / 2) / wave * wave; /* whole waves of resident frames, nearest */
         if (want < wave) want = wave;
-        if (want * 2 <= n_frames) chunk_frames = want;
+        if (want * 2 <= n_frames) {
+            /* the first and the last chunk are one wave: nothing overlaps the first chunk's input
+             * copy or the last chunk's kernels and output copy, so they are kept short */
+            u64 first = wave, last = wave;
+            if (const char *e = getenv("FLACB200_EDGE_CHUNK_FRAMES")) first = last = (u64)atoll(e) > 0 ? (u64)atoll(e) : want;
+            if (first + last >= n_frames) first = last = want;
+            u64 f = first < want ? first : want;
+            while (f + last < n_frames) {
+                chunk_f0.push_back(f);
+                f += want;
+            }
+            if (n_frames - chunk_f0.back() > last && last < want) chunk_f0.push_back(n_frames - last);
+        }
     }
-    const u64 n_chunks = (n_frames + chunk_frames - 1) / chunk_frames;
+    chunk_f0.push_back(n_frames);
+    const u64 n_chunks = chunk_f0.size() - 1;
     float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f, stage_ms[4] = {0.f, 0.f, 0.f, 0.f};
     u64 host_off = 0; /* bytes produced so far */
     int64_t bad_frame = -1;
@@ -577,6 +603,9 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     int threads = 0, smem = 0;
     int status = FLACB_OK;
 
+    const bool timeline = getenv("FLACB200_TIMELINE") != nullptr; /* development aid: when did each chunk's copies and kernels run */
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     struct Pending {
         ChunkMeta meta;
         u64 f0, nfr;
@@ -591,9 +620,16 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         if (!pd.active) return FLACB_OK;
         pd.active = false;
         CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        if (timeline) fprintf(stderr, "host: chunk f0=%llu kernels seen done at %.3f\n", (unsigned long long)pd.f0, host_ms());
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1));
         k_ms += ms;
+        if (timeline) {
+            float a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            if (host_in) cudaEventElapsedTime(&a0, c->ev_c0, sl.ev_c0), cudaEventElapsedTime(&a1, c->ev_c0, sl.ev_c1);
+            cudaEventElapsedTime(&b0, c->ev_c0, sl.ev_k0), cudaEventElapsedTime(&b1, c->ev_c0, sl.ev_k1);
+            fprintf(stderr, "chunk f0=%llu slot %d: h2d %.3f-%.3f kernels %.3f-%.3f\n", (unsigned long long)pd.f0, s, a0, a1, b0, b1);
+        }
         if (sl.staged) {
             cudaEvent_t ev[5] = {sl.ev_k0, sl.ev_s[0], sl.ev_s[1], sl.ev_s[2], sl.ev_k1};
             for (int k = 0; k < 4; k++) {
@@ -632,9 +668,12 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
                 return FLACB_OK;
             }
             if (valid) {
-                CUDA_TRY(cudaEventRecord(sl.ev_d0, sl.stream));
-                CUDA_TRY(cudaMemcpyAsync(out + host_off, sl.out.p, valid, cudaMemcpyDeviceToHost, sl.stream));
-                CUDA_TRY(cudaEventRecord(sl.ev_d1, sl.stream));
+                const double h0 = host_ms();
+                /* the chunk's kernels are done (the host has just waited for them) */
+                CUDA_TRY(cudaEventRecord(sl.ev_d0, c->d2h_stream));
+                CUDA_TRY(cudaMemcpyAsync(out + host_off, sl.out.p, valid, cudaMemcpyDeviceToHost, c->d2h_stream));
+                CUDA_TRY(cudaEventRecord(sl.ev_d1, c->d2h_stream));
+                if (timeline) fprintf(stderr, "host: d2h of chunk f0=%llu enqueued %.3f-%.3f\n", (unsigned long long)pd.f0, h0, host_ms());
                 sl.d2h_pending = true;
             }
         }
@@ -649,10 +688,15 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         EncSlot &sl = c->slot[s];
         if (!sl.d2h_pending) return FLACB_OK;
         sl.d2h_pending = false;
-        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        CUDA_TRY(cudaEventSynchronize(sl.ev_d1));
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_d0, sl.ev_d1));
         d2h_ms += ms;
+        if (timeline) {
+            float d0 = 0, d1 = 0;
+            cudaEventElapsedTime(&d0, c->ev_c0, sl.ev_d0), cudaEventElapsedTime(&d1, c->ev_c0, sl.ev_d1);
+            fprintf(stderr, "slot %d: d2h %.3f-%.3f\n", s, d0, d1);
+        }
         return FLACB_OK;
     };
 
@@ -660,6 +704,12 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     if (info) {
         if ((rc = c->slot[0].info.ensure(n_frames * (u64)channels * sizeof(flacb_subframe_info)))) return rc;
         d_info = (flacb_subframe_info *)c->slot[0].info.p;
+    }
+    if (timeline) CUDA_TRY(cudaEventRecord(c->ev_c0, c->slot[0].stream));
+    int ahead = FLACB_AHEAD;
+    if (const char *e = getenv("FLACB200_AHEAD")) { /* tuning knob */
+        const int v = atoi(e);
+        if (v >= 1 && v < FLACB_SLOTS) ahead = v;
     }
     for (u64 ci = 0; ci < n_chunks; ci++) {
         const int s = (int)(ci % FLACB_SLOTS);
@@ -669,8 +719,8 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         if ((rc = retire(s))) return rc;
         if ((rc = finish_d2h(s))) return rc;
         if (status != FLACB_OK) break;
-        const u64 f0 = ci * chunk_frames;
-        const u64 nfr = f0 + chunk_frames <= n_frames ? chunk_frames : n_frames - f0;
+        const u64 f0 = chunk_f0[ci];
+        const u64 nfr = chunk_f0[ci + 1] - f0;
         const u64 s0 = f0 * (u64)block_size;
         const u64 ns = (f0 + nfr == n_frames) ? n_sample_frames - s0 : nfr * (u64)block_size;
         EncodeArgs ca = a;
@@ -680,9 +730,12 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         if (host_in) {
             const u64 nb = ns * (u64)channels * (u64)cbytes;
             if ((rc = sl.pcm.ensure(nb))) return rc;
-            CUDA_TRY(cudaEventRecord(sl.ev_c0, sl.stream));
-            CUDA_TRY(cudaMemcpyAsync(sl.pcm.p, d_pcm, nb, cudaMemcpyHostToDevice, sl.stream));
-            CUDA_TRY(cudaEventRecord(sl.ev_c1, sl.stream));
+            if (timeline) fprintf(stderr, "host: h2d of chunk %llu enqueued at %.3f\n", (unsigned long long)ci, host_ms());
+            /* the slot's previous chunk has been retired: nothing reads sl.pcm any more */
+            CUDA_TRY(cudaEventRecord(sl.ev_c0, c->h2d_stream));
+            CUDA_TRY(cudaMemcpyAsync(sl.pcm.p, d_pcm, nb, cudaMemcpyHostToDevice, c->h2d_stream));
+            CUDA_TRY(cudaEventRecord(sl.ev_c1, c->h2d_stream));
+            CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_c1, 0));
             d_pcm = (const uint8_t *)sl.pcm.p;
         }
         uint8_t *d_out = out;
@@ -696,6 +749,11 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
         pend[s].f0 = f0;
         pend[s].nfr = nfr;
         pend[s].active = true;
+        /* Start the output copy of the chunk `ahead` behind this one now (it needs the chunk's
+         * size on the host, hence a wait for its kernels) instead of when its slot is needed
+         * again: by then the copy is done, and while the host waits here the copy engine and
+         * the SMs still have the chunks in between to work on. */
+        if (ci >= (u64)ahead && (rc = retire((int)((ci - (u64)ahead) % FLACB_SLOTS)))) return rc;
     }
     /* drain in chunk order */
     for (u64 k = 0; k < FLACB_SLOTS; k++) {
