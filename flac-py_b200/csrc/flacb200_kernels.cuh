@@ -1749,14 +1749,14 @@ static __device__ void lpc_coefficients_warp(Blk &b, int L, int P)
 /* ---- staged pipeline, stage A: fixed-predictor errors and autocorrelation of every subframe of
  * a frame -> the subframe's record in HBM.  Small shared-memory footprint (planes, windowed
  * ends), no packer state: more frames per SM than the full kernel. */
-template <int LMAX, int TB, int MINB>
+template <int LMAX, int TB, int MINB, int FIXB>
 __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
-    b.B = (int)blockDim.x;
+    b.B = FIXB ? FIXB : (int)blockDim.x; /* FIXB: the block size as a compile-time constant (the usual 288) */
     b.lane = b.tid & 31;
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;
@@ -1800,14 +1800,14 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
  * (encoder.py:387-404, :135-157) -> one SubDecision per subframe in HBM.  Same small footprint
  * as stage A plus the subframes' coefficient records; its code is the unrolled all-orders
  * filter and little else, so the instruction cache holds it. */
-template <int LMAX, int TB, int MINB, int FLAVOUR>
+template <int LMAX, int TB, int MINB, int FLAVOUR, int FIXB>
 __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
-    b.B = (int)blockDim.x;
+    b.B = FIXB ? FIXB : (int)blockDim.x;
     b.lane = b.tid & 31;
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;
@@ -1909,15 +1909,16 @@ __global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p
  * CHOSEN = false: fixed predictors only (max_lpc_order == 0): the fixed-predictor errors and the
  *                 choice are computed here as well; nothing else is launched.
  * TB / MINB: launch bounds.  <576, 1> for frames that fill an SM's shared memory on their own,
- * <288, 3> (72 registers) where three frames fit an SM. */
-template <int LMAX, int TB, int MINB, bool CHOSEN>
+ * <288, 3> (72 registers) where three frames fit an SM.  FIXB: the actual block size when it is
+ * known at compile time (288, the block-4608 configurations), else 0. */
+template <int LMAX, int TB, int MINB, bool CHOSEN, int FIXB>
 __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
-    b.B = (int)blockDim.x;
+    b.B = FIXB ? FIXB : (int)blockDim.x;
     b.lane = b.tid & 31;
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;

@@ -33,29 +33,44 @@ cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour
     constexpr int LM = FLACB_TU_LMAX;
     switch (kind) {
     case K_ANALYSE:
-        return variant ? launch_one(analyse_kernel<LM, 288, 3>, grid, threads, smem, stream, p)
-                       : launch_one(analyse_kernel<LM, 576, 1>, grid, threads, smem, stream, p);
+        if (variant && threads == 288) return launch_one(analyse_kernel<LM, 288, 3, 288>, grid, threads, smem, stream, p);
+#if FLACB_TU_LMAX == 32 /* block 16384: 512-thread frames */
+        if (!variant && threads == 512) return launch_one(analyse_kernel<LM, 576, 1, 512>, grid, threads, smem, stream, p);
+#endif
+        return variant ? launch_one(analyse_kernel<LM, 288, 3, 0>, grid, threads, smem, stream, p)
+                       : launch_one(analyse_kernel<LM, 576, 1, 0>, grid, threads, smem, stream, p);
     case K_CHOOSE:
         switch (flavour) {
         case 0:
-            return variant ? launch_one(choose_kernel<LM, 288, 3, 0>, grid, threads, smem, stream, p)
-                           : launch_one(choose_kernel<LM, 576, 1, 0>, grid, threads, smem, stream, p);
+            if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 0, 288>, grid, threads, smem, stream, p);
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 0, 0>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 0, 0>, grid, threads, smem, stream, p);
         case 1:
-            return variant ? launch_one(choose_kernel<LM, 288, 3, 1>, grid, threads, smem, stream, p)
-                           : launch_one(choose_kernel<LM, 576, 1, 1>, grid, threads, smem, stream, p);
+            if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 1, 288>, grid, threads, smem, stream, p);
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 1, 0>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 1, 0>, grid, threads, smem, stream, p);
         default:
-            return variant ? launch_one(choose_kernel<LM, 288, 3, 2>, grid, threads, smem, stream, p)
-                           : launch_one(choose_kernel<LM, 576, 1, 2>, grid, threads, smem, stream, p);
+            if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 2, 288>, grid, threads, smem, stream, p);
+#if FLACB_TU_LMAX == 32 /* block 16384, 24-bit: 256-thread frames */
+            if (variant && threads == 256) return launch_one(choose_kernel<LM, 288, 3, 2, 256>, grid, threads, smem, stream, p);
+#endif
+            return variant ? launch_one(choose_kernel<LM, 288, 3, 2, 0>, grid, threads, smem, stream, p)
+                           : launch_one(choose_kernel<LM, 576, 1, 2, 0>, grid, threads, smem, stream, p);
         }
     case K_SERIALISE:
-        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, true>, grid, threads, smem, stream, p)
-                       : launch_one(encode_frames_kernel<LM, 576, 1, true>, grid, threads, smem, stream, p);
+        if (variant && threads == 288) return launch_one(encode_frames_kernel<LM, 288, 3, true, 288>, grid, threads, smem, stream, p);
+#if FLACB_TU_LMAX == 32
+        if (!variant && threads == 512) return launch_one(encode_frames_kernel<LM, 576, 1, true, 512>, grid, threads, smem, stream, p);
+#endif
+        return variant ? launch_one(encode_frames_kernel<LM, 288, 3, true, 0>, grid, threads, smem, stream, p)
+                       : launch_one(encode_frames_kernel<LM, 576, 1, true, 0>, grid, threads, smem, stream, p);
     default: return cudaErrorInvalidValue;
     }
 #else
     if (kind != K_FIXED) return cudaErrorInvalidValue;
-    return variant ? launch_one(encode_frames_kernel<12, 288, 3, false>, grid, threads, smem, stream, p)
-                   : launch_one(encode_frames_kernel<12, 576, 1, false>, grid, threads, smem, stream, p);
+    if (variant && threads == 288) return launch_one(encode_frames_kernel<12, 288, 3, false, 288>, grid, threads, smem, stream, p);
+    return variant ? launch_one(encode_frames_kernel<12, 288, 3, false, 0>, grid, threads, smem, stream, p)
+                   : launch_one(encode_frames_kernel<12, 576, 1, false, 0>, grid, threads, smem, stream, p);
 #endif
 }
 
@@ -72,9 +87,9 @@ size_t FLACB_CAT(static_smem_, FLACB_TU_NAME)()
 {
     cudaFuncAttributes fa;
 #if FLACB_TU_LMAX
-    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, true>) != cudaSuccess) return 8192;
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, true, 0>) != cudaSuccess) return 8192;
 #else
-    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1, false>) != cudaSuccess) return 8192;
+    if (cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1, false, 0>) != cudaSuccess) return 8192;
 #endif
     return fa.sharedSizeBytes;
 }

@@ -119,9 +119,9 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         pa.all_planes = front_planes;
         for (uint64_t f = 0; f < n_frames; f++) {
             if (max_lpc_order <= 12)
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<12, 576, 1>(pa); });
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<12, 576, 1, 0>(pa); });
             else
-                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<32, 576, 1>(pa); });
+                sim::run_block((unsigned)f, (unsigned)n_frames, B, pa.lay.total, [&]() { analyse_kernel<32, 576, 1, 0>(pa); });
         }
         const int wpb = 4;
         const unsigned nb = (unsigned)((n_sub + wpb - 1) / wpb);
@@ -142,24 +142,24 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         for (uint64_t f = 0; f < n_frames; f++) {
             const unsigned fu = (unsigned)f, g = (unsigned)n_frames;
             if (max_lpc_order <= 12) {
-                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 0>(pc); });
-                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 1>(pc); });
-                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 2>(pc); });
+                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 0, 0>(pc); });
+                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 1, 0>(pc); });
+                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 2, 0>(pc); });
             } else {
-                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 0>(pc); });
-                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 1>(pc); });
-                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 2>(pc); });
+                if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 0, 0>(pc); });
+                else if (flavour == 1) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 1, 0>(pc); });
+                else sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<32, 576, 1, 2, 0>(pc); });
             }
         }
     }
     const size_t dyn = p.lay.total;
     for (uint64_t f = 0; f < n_frames; f++) {
         if (!staged)
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, false>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, false, 0>(p); });
         else if (max_lpc_order <= 12)
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, true>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, true, 0>(p); });
         else
-            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, true>(p); });
+            sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<32, 576, 1, true, 0>(p); });
     }
     if (flags & FLACB_SLOT_COMPACT) {
         sim::run_block(0, 1, 256, 0, [&]() { scan_frame_bytes_kernel(frame_bytes.data(), frame_off.data(), (uint32_t)n_frames); });
