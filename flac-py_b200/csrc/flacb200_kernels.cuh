@@ -1211,15 +1211,19 @@ static __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
     }
     __syncthreads();
     /* sum over samples of (u >> k) for every candidate order (rice_size, encoder.py:756-760);
-     * u >> k < 2^29 for bps <= 24, so a thread's tile sum fits 32 bits */
+     * u >> k < 2^29 for bps <= 24, so a thread's tile sum fits 32 bits.  The candidate orders are
+     * consecutive (both admission tests are monotone in the order) and their partitions nest, so
+     * a run that lies in one partition of the finest order lies in one partition of every order,
+     * whose index is the finest one shifted: one pass over the residual serves up to RG orders. */
     u64 lane_q = 0;
+    constexpr int RG = 6;
+    const int o_last = (int)sh.cand_o[ncand - 1];
+    const uint32_t psz_f = (uint32_t)n >> o_last, magic_f = sh.cand_magic[ncand - 1];
 #pragma unroll 1
-    for (int ci = 0; ci < ncand; ci++) {
-        const uint32_t o = sh.cand_o[ci];
-        const uint32_t psz = (uint32_t)n >> o;
-        const uint32_t magic = sh.cand_magic[ci];
-        const uint8_t *kk = b.kall + (1u << o);
-        u64 acc = 0;
+    for (int g0 = 0; g0 < ncand; g0 += RG) {
+        u64 acc[RG];
+#pragma unroll
+        for (int j = 0; j < RG; j++) acc[j] = 0;
 #pragma unroll 1
         for (int tile = 0; tile < b.ntiles; tile++) {
             const int i0 = (tile * b.B + b.tid) * E;
@@ -1229,23 +1233,43 @@ static __device__ void rice_search(Blk &b, Decision &d, uint32_t *res_bits)
                 uint32_t u[E];
 #pragma unroll
                 for (int e = 0; e < E; e++) u[e] = (uint32_t)ui[e];
-                const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
-                const uint32_t bnd = (p0 + 1) * psz;
-                uint32_t t32 = 0;
-                if ((uint32_t)(i0 + E) <= bnd) { /* the run lies in one partition (the usual case) */
-                    const uint32_t k0 = kk[p0];
+                const uint32_t p0 = fast_div((uint32_t)i0, psz_f, magic_f);
+                if ((uint32_t)(i0 + E) <= (p0 + 1) * psz_f) { /* the run lies in one partition (the usual case) */
 #pragma unroll
-                    for (int e = 0; e < E; e++) t32 += u[e] >> k0;
+                    for (int j = 0; j < RG; j++) {
+                        if (g0 + j < ncand) {
+                            const int o = (int)sh.cand_o[g0 + j];
+                            const uint32_t k0 = b.kall[(1u << o) + (p0 >> (o_last - o))];
+                            uint32_t t32 = 0;
+#pragma unroll
+                            for (int e = 0; e < E; e++) t32 += u[e] >> k0;
+                            acc[j] += t32;
+                        }
+                    }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < E; e++)
-                        if (i0 + e < n) t32 += u[e] >> kk[fast_div((uint32_t)(i0 + e), psz, magic)];
+                    for (int j = 0; j < RG; j++) {
+                        if (g0 + j < ncand) {
+                            const uint32_t o = sh.cand_o[g0 + j];
+                            const uint32_t psz = (uint32_t)n >> o, magic = sh.cand_magic[g0 + j];
+                            const uint8_t *kk = b.kall + (1u << o);
+                            uint32_t t32 = 0;
+#pragma unroll
+                            for (int e = 0; e < E; e++)
+                                if (i0 + e < n) t32 += u[e] >> kk[fast_div((uint32_t)(i0 + e), psz, magic)];
+                            acc[j] += t32;
+                        }
+                    }
                 }
-                acc += t32;
             }
         }
-        const u64 t = warp_sum_u64(acc);
-        if (b.lane == ci) lane_q = t;
+#pragma unroll
+        for (int j = 0; j < RG; j++) {
+            if (g0 + j < ncand) { /* block-uniform */
+                const u64 t = warp_sum_u64(acc[j]);
+                if (b.lane == g0 + j) lane_q = t;
+            }
+        }
     }
     if (b.lane < MAX_CAND) b.red[b.warp * RED_STRIDE + b.lane] = lane_q;
     __syncthreads();
