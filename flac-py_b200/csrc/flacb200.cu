@@ -577,13 +577,17 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     if (host_in && host_out && !info && !(flags & FLACB_SLOT_COMPACT)) {
         const u64 wave = (u64)c->sm_count * (u64)plan.shape.ctas_per_sm;
         u64 want = (16ull << 20) / (frame_pcm ? frame_pcm : 1);
-        if (const char *e = getenv("FLACB200_CHUNK_FRAMES")) want = (u64)atoll(e);
         want = (want + wave / 2) / wave * wave; /* whole waves of resident frames, nearest */
         if (want < wave) want = wave;
+        u64 edge = wave;
+        if (const char *e = getenv("FLACB200_CHUNK_FRAMES")) { /* tuning / test knob: taken as it is */
+            want = (u64)atoll(e) > 0 ? (u64)atoll(e) : 1;
+            if (edge > want) edge = want;
+        }
         if (want * 2 <= n_frames) {
             /* the first and the last chunk are one wave: nothing overlaps the first chunk's input
              * copy or the last chunk's kernels and output copy, so they are kept short */
-            u64 first = wave, last = wave;
+            u64 first = edge, last = edge;
             if (const char *e = getenv("FLACB200_EDGE_CHUNK_FRAMES")) first = last = (u64)atoll(e) > 0 ? (u64)atoll(e) : want;
             if (first + last >= n_frames) first = last = want;
             u64 f = first < want ? first : want;

@@ -150,20 +150,22 @@ def test_large_config2_slice_round_trip_and_oracle_spot_check():
 
 
 def test_chunked_host_pipeline_matches_single_launch(monkeypatch):
-    """host buffers: the library cuts the frame range into chunks with three in flight (H2D,
-    kernel, D2H overlapped); bytes, offsets and error position must not depend on the cut"""
+    """host buffers: the library cuts the frame range into chunks with several in flight (H2D,
+    kernels, D2H overlapped, one stream per copy direction); bytes, offsets and error position
+    must not depend on the cut (FLACB200_CHUNK_FRAMES is taken as it is: 71 frames in chunks
+    of 5 / 16 / 33 / one chunk)"""
     from flac import _native as N
     x = S.pcm(4608 * 70 + 999, 2, 16, 44100, "mixed", 0xF1AC0002)
     p = _params(CASES["c2_white"])
     ref = O.encode_frames(x, 16, 4608, 12, 5, 0, 5, threads=8)
-    for chunk in ("444", "888", "100000"):
+    for chunk in ("5", "16", "33", "100000"):
         monkeypatch.setenv("FLACB200_CHUNK_FRAMES", chunk)
         sh, _ = _encode(x, 16, p)
         assert sh.rc == 0 and sh.out.tobytes() == ref.data and (sh.offs == ref.frame_offsets).all(), chunk
     # an out-of-domain frame (digital silence) in the third chunk: everything in front of it is returned
     y = x.copy()
     y[4608 * 50:4608 * 51] = 0
-    monkeypatch.setenv("FLACB200_CHUNK_FRAMES", "444")
+    monkeypatch.setenv("FLACB200_CHUNK_FRAMES", "16")
     sh, _ = _encode(y, 16, p)
     assert sh.rc == N.E_ZERODIV and sh.stats.first_bad_frame == 50
     assert sh.out.tobytes() == O.encode_frames(y[:4608 * 50], 16, 4608, 12, 5, 0, 5, threads=8).data
