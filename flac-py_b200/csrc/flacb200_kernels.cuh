@@ -1076,23 +1076,27 @@ __device__ void residual_and_cum(Blk &b, const int32_t *x, const Decision &d, in
                     u[e] = (int)(((uint32_t)rr << 1) ^ (uint32_t)(rr >> 31));
                 }
             } else {
-                i64 acc[E];
+                /* four samples at a time: half the 64-bit accumulators live at once */
 #pragma unroll
-                for (int e = 0; e < E; e++) acc[e] = 0;
+                for (int e0 = 0; e0 < E; e0 += 4) {
+                    i64 acc[4];
 #pragma unroll
-                for (int j = 0; j < LMAX; j++) {
-                    if (j < d.ncoef) {
-                        const i64 cj = d.q[j];
+                    for (int e = 0; e < 4; e++) acc[e] = 0;
 #pragma unroll
-                        for (int e = 0; e < E; e++) acc[e] += (i64)h[LMAX + e - 1 - j] * cj;
+                    for (int j = 0; j < LMAX; j++) {
+                        if (j < d.ncoef) {
+                            const i64 cj = d.q[j];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) acc[e] += (i64)h[LMAX + e0 + e - 1 - j] * cj;
+                        }
                     }
-                }
 #pragma unroll
-                for (int e = 0; e < E; e++) {
-                    const i64 r = (i64)h[LMAX + e] - (acc[e] >> d.shift);
-                    const u64 z = ((u64)r << 1) ^ (u64)(r >> 63);
-                    if ((z >> 32) != 0 && i0 + e >= d.warm && i0 + e < n) range_bad = true;
-                    u[e] = (int)(uint32_t)z;
+                    for (int e = 0; e < 4; e++) {
+                        const i64 r = (i64)h[LMAX + e0 + e] - (acc[e] >> d.shift);
+                        const u64 z = ((u64)r << 1) ^ (u64)(r >> 63);
+                        if ((z >> 32) != 0 && i0 + e0 + e >= d.warm && i0 + e0 + e < n) range_bad = true;
+                        u[e0 + e] = (int)(uint32_t)z;
+                    }
                 }
             }
 #pragma unroll
@@ -1475,42 +1479,49 @@ static __device__ void pack_residual(Blk &b, const Decision &d)
     const uint32_t magic = psz == 1 ? 0u : 0xFFFFFFFFu / psz + 1u;
     const uint8_t *kk = b.kall + (1u << d.porder);
     const uint32_t method_code = d.method == 4 ? 0u : 1u;
+    const uint32_t hv = (method_code << 4) | (uint32_t)d.porder; /* encoder.py:766-767 */
+    /* parameter of sample i's partition and the prefix bits in front of its code: the parameter
+     * field at the start of a partition, method + partition order in front of the first one */
+    auto param_of = [&](int i, uint32_t &k, uint32_t &pre) {
+        const uint32_t pi = fast_div((uint32_t)i, psz, magic);
+        const uint32_t pstart = pi * psz < (uint32_t)d.warm ? (uint32_t)d.warm : pi * psz;
+        k = kk[pi];
+        pre = (uint32_t)i == pstart ? (uint32_t)d.method + (i == d.warm ? 6u : 0u) : 0u;
+    };
     for (int tile = 0; tile < b.ntiles; tile++) {
         const int i0 = (tile * b.B + b.tid) * E;
-        uint32_t u[E], k[E], pre[E]; /* pre: number of prefix bits in front of the code */
+        uint32_t u[E];
         uint32_t nbits = 0;
-        int ui[E];
-        if (i0 < n) {
-            ld_run<E>((const int32_t *)b.res, (uint32_t)i0, ui);
-        } else {
+        {
+            int ui[E];
+            if (i0 < n) {
+                ld_run<E>((const int32_t *)b.res, (uint32_t)i0, ui);
+            } else {
 #pragma unroll
-            for (int e = 0; e < E; e++) ui[e] = 0;
-        }
-        const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
-        if (i0 >= d.warm && i0 + E <= n && (uint32_t)(i0 + E) <= (p0 + 1) * psz) {
-            /* the usual run: inside the block, behind the warm-up, in one partition; only its
-             * first sample can open the partition */
-            const uint32_t k0 = kk[p0];
-            const uint32_t pstart = p0 * psz < (uint32_t)d.warm ? (uint32_t)d.warm : p0 * psz;
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-                u[e] = (uint32_t)ui[e], k[e] = k0, pre[e] = 0;
-                nbits += (u[e] >> k0) + 1u + k0;
+                for (int e = 0; e < E; e++) ui[e] = 0;
             }
-            if ((uint32_t)i0 == pstart) pre[0] = (uint32_t)d.method + (i0 == d.warm ? 6u : 0u);
-            nbits += pre[0];
+#pragma unroll
+            for (int e = 0; e < E; e++) u[e] = (uint32_t)ui[e];
+        }
+        /* the usual run: inside the block, behind the warm-up, in one partition; only its first
+         * sample can open the partition.  Such a thread carries one parameter over the scan; the
+         * few others look theirs up again per sample. */
+        const uint32_t p0 = fast_div((uint32_t)i0, psz, magic);
+        const bool usual = i0 >= d.warm && i0 + E <= n && (uint32_t)(i0 + E) <= (p0 + 1) * psz;
+        uint32_t k0 = 0, pre0 = 0;
+        if (usual) {
+            param_of(i0, k0, pre0);
+#pragma unroll
+            for (int e = 0; e < E; e++) nbits += (u[e] >> k0) + 1u + k0;
+            nbits += pre0;
         } else {
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 const int i = i0 + e;
-                u[e] = 0, k[e] = 0, pre[e] = 0;
                 if (i >= d.warm && i < n) {
-                    const uint32_t pi = fast_div((uint32_t)i, psz, magic);
-                    const uint32_t pstart = pi * psz < (uint32_t)d.warm ? (uint32_t)d.warm : pi * psz;
-                    u[e] = (uint32_t)ui[e];
-                    k[e] = kk[pi];
-                    if ((uint32_t)i == pstart) pre[e] = (uint32_t)d.method + (i == d.warm ? 6u : 0u);
-                    nbits += pre[e] + (u[e] >> k[e]) + 1u + k[e];
+                    uint32_t k, pre;
+                    param_of(i, k, pre);
+                    nbits += pre + (u[e] >> k) + 1u + k;
                 }
             }
         }
@@ -1525,28 +1536,40 @@ static __device__ void pack_residual(Blk &b, const Decision &d)
             const uint32_t wbase = sh.wbase;
             /* uniform: the whole tile lies inside the window, no range checks needed */
             const bool fits = (sh.pos >> 5) >= wbase && (tile_end >> 5) + 1u < wbase + b.stg_words;
+            auto put = [&](uint32_t bp, uint32_t v, int nb) {
+                if (fits) or_bits<false>(b.stg, wbase, b.stg_words, bp, v, nb);
+                else or_bits<true>(b.stg, wbase, b.stg_words, bp, v, nb);
+            };
             if (nbits) {
                 uint32_t cur = p_start;
+                if (usual) {
+                    if (pre0) {
+                        if (pre0 > (uint32_t)d.method) put(cur, hv, 6), cur += 6;
+                        put(cur, k0, d.method); /* encoder.py:791 */
+                        cur += (uint32_t)d.method;
+                    }
 #pragma unroll
-                for (int e = 0; e < E; e++) {
-                    const int i = i0 + e;
-                    if (i >= d.warm && i < n) {
-                        if (pre[e]) {
-                            if (pre[e] > (uint32_t)d.method) {
-                                const uint32_t hv = (method_code << 4) | (uint32_t)d.porder; /* encoder.py:766-767 */
-                                if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, hv, 6);
-                                else or_bits<true>(b.stg, wbase, b.stg_words, cur, hv, 6);
-                                cur += 6;
+                    for (int e = 0; e < E; e++) {
+                        cur += u[e] >> k0; /* q zeros: the window is pre-zeroed (encoder.py:802) */
+                        put(cur, (1u << k0) | (u[e] & ((1u << k0) - 1u)), (int)k0 + 1);
+                        cur += k0 + 1u;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const int i = i0 + e;
+                        if (i >= d.warm && i < n) {
+                            uint32_t k, pre;
+                            param_of(i, k, pre);
+                            if (pre) {
+                                if (pre > (uint32_t)d.method) put(cur, hv, 6), cur += 6;
+                                put(cur, k, d.method);
+                                cur += (uint32_t)d.method;
                             }
-                            if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, k[e], d.method); /* encoder.py:791 */
-                            else or_bits<true>(b.stg, wbase, b.stg_words, cur, k[e], d.method);
-                            cur += (uint32_t)d.method;
+                            cur += u[e] >> k;
+                            put(cur, (1u << k) | (u[e] & ((1u << k) - 1u)), (int)k + 1);
+                            cur += k + 1u;
                         }
-                        cur += u[e] >> k[e]; /* q zeros: the window is pre-zeroed (encoder.py:802) */
-                        const uint32_t cv = (1u << k[e]) | (u[e] & ((1u << k[e]) - 1u));
-                        if (fits) or_bits<false>(b.stg, wbase, b.stg_words, cur, cv, (int)k[e] + 1);
-                        else or_bits<true>(b.stg, wbase, b.stg_words, cur, cv, (int)k[e] + 1);
-                        cur += k[e] + 1u;
                     }
                 }
             }
