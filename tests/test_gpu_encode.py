@@ -135,6 +135,25 @@ def test_against_oracle_on_fresh_inputs(bits, cls, L, bs):
     assert (sh.offs == ref.frame_offsets).all()
 
 
+@pytest.mark.parametrize("ch,bits,L,q,bs,cls", [(3, 16, 12, 12, 2304, "mixed"), (5, 24, 8, 9, 1024, "white"),
+                                                (1, 16, 12, 8, 4608, "white"), (6, 20, 12, 5, 576, "mixed"),
+                                                (2, 12, 4, 5, 192, "white"), (4, 24, 32, 14, 4096, "white")])
+def test_other_channel_counts_widths_and_precisions_against_the_oracle(ch, bits, L, q, bs, cls):
+    """3 / 5 / 6 / 4 channels, 12 / 20-bit samples, precisions 8 (coefficient bytes at full range),
+    9, 12, 14 (the 32/64-bit flavour of the all-orders filter), short blocks; many frames"""
+    x = S.pcm(bs * 40 + bs // 3 + 5, ch, bits, 48000, cls, 99 + ch + bits)
+    from flac.encoder import EncoderParameters
+    p = EncoderParameters(block_size=bs, rice_partition_order=range(0, 5), lpc_order=range(L + 1), qlp_precision=q)
+    try:
+        ref = O.encode_frames(x, bits, bs, L, q, 0, 4, threads=8)
+    except O.OracleError:
+        pytest.skip("input outside the reference's domain")
+    sh, _ = _encode(x, bits, p)
+    assert sh.rc == 0
+    assert sh.out.tobytes() == ref.data
+    assert (sh.offs == ref.frame_offsets).all()
+
+
 def test_large_config2_slice_round_trip_and_oracle_spot_check():
     """60 s of config-2 audio: oracle bytes on a slice, oracle decode of the whole"""
     n = 44100 * 60
