@@ -145,8 +145,11 @@ def pcm(n: int, channels: int, bits: int = 16, rate: int = 44100, cls: str = "mi
 
 
 def pack_le(samples: np.ndarray, bits: int) -> bytes:
-    """Interleaved int32 (n, channels) -> little-endian packed PCM bytes (WAV payload)."""
+    """Interleaved int32 (n, channels) -> little-endian packed PCM bytes (WAV payload): containers
+    of ceil(bits / 8) bytes, sign extended (12-bit samples travel in 2 bytes, 20-bit in 3)."""
     a = np.ascontiguousarray(samples, dtype=np.int32)
+    if bits not in (8, 16, 24, 32) and 4 <= bits <= 32:
+        return pack_le(a, 8 * ((bits + 7) // 8))
     if bits == 16:
         return a.astype("<i2").tobytes()
     if bits == 24:
