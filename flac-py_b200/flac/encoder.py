@@ -88,6 +88,26 @@ def complete_streaminfo(streaminfo: bytes, frame_lengths, pcm_le: Optional[bytes
     return bytes(out)
 
 
+def seektable_block(frame_offsets, block_size: int, total_samples: int, every: int = 10,
+                    last: bool = True) -> bytes:
+    """A SEEKTABLE metadata block (type 3, common.py:30) from the frame byte offsets the encode
+    returns anyway: one seek point per `every` frames (first sample of the frame, byte offset from
+    the first frame header, samples in the frame).  An extension:
+    the reference never writes one, its decoder skips it (decoder.py:43-44, :92-97), and so does
+    this package's.  To use it, clear the "last" bit of the STREAMINFO header (first byte of the
+    second chunk of `stream_prologue`: 0x80 -> 0x00) and put this block in front of the frames."""
+    offs = [int(v) for v in frame_offsets]
+    n_frames = len(offs) - 1
+    points = bytearray()
+    for f in range(0, n_frames, max(1, int(every))):
+        first = f * block_size
+        count = min(block_size, total_samples - first)
+        points += first.to_bytes(8, "big") + offs[f].to_bytes(8, "big") + count.to_bytes(2, "big")
+    assert len(points) < (1 << 24)
+    header = bytes([(0x80 if last else 0x00) | 3]) + len(points).to_bytes(3, "big")
+    return header + bytes(points)
+
+
 class _Shard:
     """Frames [f0, f1) of one call on one device."""
 

@@ -145,3 +145,26 @@ def test_complete_streaminfo_fills_frame_sizes_and_md5():
     assert int.from_bytes(out[4:7], "big") == 14 and int.from_bytes(out[7:10], "big") == 9000
     assert out[18:] == hashlib.md5(pcm).digest()
     assert complete_streaminfo(block, []) == block
+
+
+def test_seektable_block_is_skipped_by_the_decoder_and_points_at_frames():
+    """extension: a SEEKTABLE block built from the frame offsets; the
+    reference's decoder (here: its restatement) skips it and decodes the same PCM, and every seek
+    point lands on a frame sync code"""
+    from flac.encoder import seektable_block
+    import flacb200_synth as S
+    import oracle as O
+    x = S.pcm(1000 * 7 + 333, 2, 16, 44100, "white", 5)
+    enc = O.encode_frames(x, 16, 1000, 8, 6, 0, 3)
+    pro = bytearray(O.stream_prologue(44100, 2, 16, x.shape[0], 1000))
+    assert pro[4] == 0x80
+    pro[4] = 0x00                                             # STREAMINFO is no longer the last block
+    block = seektable_block(enc.frame_offsets, 1000, x.shape[0], every=3)
+    assert block[0] == 0x83 and int.from_bytes(block[1:4], "big") == 18 * 3
+    stream = bytes(pro) + block + enc.data
+    assert (O.decode_stream(stream)[4] == x).all()
+    for k in range(3):
+        p = block[4 + 18 * k:4 + 18 * (k + 1)]
+        sample, off, count = int.from_bytes(p[:8], "big"), int.from_bytes(p[8:16], "big"), int.from_bytes(p[16:], "big")
+        assert sample == 3 * k * 1000 and enc.data[off:off + 2] == b"\xff\xf8"
+        assert count == (1000 if 3 * k < 7 else 333)
