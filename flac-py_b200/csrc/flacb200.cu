@@ -371,6 +371,11 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
             return (size_t)make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, threads, all_planes).total;
         };
         if (!small_shape(front_total, plan.front, true) || !small_shape(choose_total, plan.choose, false)) return FLACB_E_UNSUPPORTED;
+        /* the all-orders filter needs no more than 56 registers: four 288-thread frames per SM
+         * when their planes and coefficient records fit */
+        if (plan.choose.variant == 1 && plan.choose.threads == 288 &&
+            4 * (choose_total(288, plan.choose.all_planes) + plan.static_smem + 1024) <= 228 * 1024)
+            plan.choose.variant = 2, plan.choose.ctas_per_sm = 4;
         shape_from_env("FLACB200_SHAPE_A", plan.front, plan.static_smem, (size_t)c->smem_optin, front_total);
         shape_from_env("FLACB200_SHAPE_C1", plan.choose, plan.static_smem, (size_t)c->smem_optin, choose_total);
     }

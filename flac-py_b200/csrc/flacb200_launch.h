@@ -19,7 +19,8 @@ enum KernelKind {
     K_SERIALISE = 3  /* stage C2: encode_frames_kernel<.., true>                                 */
 };
 
-/* variant 0: <576, 1> launch bounds, 1: <288, 3> (72 registers); flavour: lpc_errors_rolled's, K_CHOOSE only */
+/* variant 0: <576, 1> launch bounds, 1: <288, 3> (72 registers), 2: <288, 4> (56 registers, K_CHOOSE with
+ * 288 threads only); flavour: lpc_errors_rolled's, K_CHOOSE only */
 #define FLACB_TU_DECL(name)                                                                                        \
     cudaError_t launch_##name(int kind, int variant, int flavour, unsigned grid, int threads, size_t smem,         \
                               cudaStream_t stream, const EncParams &p);                                            \

@@ -42,14 +42,17 @@ cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour
     case K_CHOOSE:
         switch (flavour) {
         case 0:
+            if (variant == 2 && threads == 288) return launch_one(choose_kernel<LM, 288, 4, 0, 288>, grid, threads, smem, stream, p);
             if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 0, 288>, grid, threads, smem, stream, p);
             return variant ? launch_one(choose_kernel<LM, 288, 3, 0, 0>, grid, threads, smem, stream, p)
                            : launch_one(choose_kernel<LM, 576, 1, 0, 0>, grid, threads, smem, stream, p);
         case 1:
+            if (variant == 2 && threads == 288) return launch_one(choose_kernel<LM, 288, 4, 1, 288>, grid, threads, smem, stream, p);
             if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 1, 288>, grid, threads, smem, stream, p);
             return variant ? launch_one(choose_kernel<LM, 288, 3, 1, 0>, grid, threads, smem, stream, p)
                            : launch_one(choose_kernel<LM, 576, 1, 1, 0>, grid, threads, smem, stream, p);
         default:
+            if (variant == 2 && threads == 288) return launch_one(choose_kernel<LM, 288, 4, 2, 288>, grid, threads, smem, stream, p);
             if (variant && threads == 288) return launch_one(choose_kernel<LM, 288, 3, 2, 288>, grid, threads, smem, stream, p);
 #if FLACB_TU_LMAX == 32 /* block 16384, 24-bit: 256-thread frames */
             if (variant && threads == 256) return launch_one(choose_kernel<LM, 288, 3, 2, 256>, grid, threads, smem, stream, p);
