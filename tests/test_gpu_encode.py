@@ -137,10 +137,12 @@ def test_against_oracle_on_fresh_inputs(bits, cls, L, bs):
 
 @pytest.mark.parametrize("ch,bits,L,q,bs,cls", [(3, 16, 12, 12, 2304, "mixed"), (5, 24, 8, 9, 1024, "white"),
                                                 (1, 16, 12, 8, 4608, "white"), (6, 20, 12, 5, 576, "mixed"),
-                                                (2, 12, 4, 5, 192, "white"), (4, 24, 32, 14, 4096, "white")])
+                                                (2, 12, 4, 5, 192, "white"), (4, 24, 32, 14, 4096, "white"),
+          (2, 16, 32, 5, 4096, "white"), (2, 16, 32, 8, 1024, "white")])
 def test_other_channel_counts_widths_and_precisions_against_the_oracle(ch, bits, L, q, bs, cls):
     """3 / 5 / 6 / 4 channels, 12 / 20-bit samples, precisions 8 (coefficient bytes at full range),
-    9, 12, 14 (the 32/64-bit flavour of the all-orders filter), short blocks; many frames"""
+    9, 12, 14 (the 32/64-bit flavour of the all-orders filter), order 32 on 16-bit samples (dp2a bodies
+    up to 32 wide), short blocks; many frames"""
     x = S.pcm(bs * 40 + bs // 3 + 5, ch, bits, 48000, cls, 99 + ch + bits)
     from flac.encoder import EncoderParameters
     p = EncoderParameters(block_size=bs, rice_partition_order=range(0, 5), lpc_order=range(L + 1), qlp_precision=q)

@@ -52,13 +52,15 @@ def test_sim_all_orders_filter_flavours_agree(name):
 
 
 SHAPES = [(3, 16, 12, 12, 2304, "mixed"), (5, 24, 8, 9, 1024, "white"), (1, 16, 12, 8, 4608, "white"),
-          (6, 20, 12, 5, 576, "mixed"), (2, 12, 4, 5, 192, "white"), (4, 24, 32, 14, 4096, "white")]
+          (6, 20, 12, 5, 576, "mixed"), (2, 12, 4, 5, 192, "white"), (4, 24, 32, 14, 4096, "white"),
+          (2, 16, 32, 5, 4096, "white"), (2, 16, 32, 8, 1024, "white")]
 
 
 @pytest.mark.parametrize("ch,bits,L,q,bs,cls", SHAPES)
 def test_sim_other_channel_counts_widths_and_precisions_against_the_oracle(ch, bits, L, q, bs, cls):
     """3 / 5 / 6 / 4 channels, 12 / 20-bit samples, precisions 8 (coefficient bytes at full range),
-    9, 12, 14 (the 32/64-bit flavour of the all-orders filter), short blocks"""
+    9, 12, 14 (the 32/64-bit flavour of the all-orders filter), order 32 on 16-bit samples (dp2a bodies
+    up to 32 wide), short blocks"""
     import flacb200_synth as S
     x = S.pcm(bs * 3 + bs // 3 + 5, ch, bits, 48000, cls, 99 + ch + bits)
     ref = O.encode_frames(x, bits, bs, L, q, 0, 4)
