@@ -48,3 +48,17 @@ def case_kwargs(case: dict) -> dict:
 
 def ood_pcm(case: dict) -> np.ndarray:
     return np.load(os.path.join(GOLDEN, case["name"] + ".npy")).astype(np.int32)
+
+
+with open(os.path.join(GOLDEN, "decode_cases.json")) as _f:
+    DECODE_CASES = {k: v for k, v in json.load(_f).items() if not k.startswith("_")}
+
+STATUS_NAMES = {0: None, 1: "AssertionError", 2: "ValueError", 3: "ZeroDivisionError", 4: "EOFError",
+                6: "OverflowError", 7: "KeyError"}
+
+
+def decode_case(case: dict) -> tuple[bytes, np.ndarray]:
+    """-> (stream, samples the reference decoder yields before it returns or raises)"""
+    rows = case["samples"]
+    want = np.array(rows, dtype=np.int64).reshape(len(rows), -1) if rows else np.zeros((0, 0), dtype=np.int64)
+    return bytes.fromhex(case["stream"]), want

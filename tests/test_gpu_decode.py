@@ -131,3 +131,24 @@ def test_decode_variable_block_sizes():
     frames = O.encode_frames(a, 16, 1000, 8, 6, 0, 3).data + O.encode_frames(b, 16, 4096, 8, 6, 0, 3).data
     pcm, fch = decode_frames(frames, 16)
     assert fch == 2 and (pcm == np.concatenate([a, b])).all()
+
+
+@pytest.mark.parametrize("name", sorted(__import__("helpers").DECODE_CASES))
+def test_crafted_streams_decode_like_the_reference(name):
+    """constant / verbatim subframes, escaped partitions, 5-bit Rice method, wasted-bits flag,
+    L/S, S/R, M/S, 3 channels, reserved type, negative LPC shift: through flac.decoder.decode, the
+    samples the reference decoder yields and the exception it ends with (fixtures from the real
+    reference, tests/golden/make_decode_golden.py)"""
+    from flac.decoder import decode
+    from helpers import DECODE_CASES, decode_case
+    case = DECODE_CASES[name]
+    stream, want = decode_case(case)
+    rate, bits, ch, total, samples = decode(io.BytesIO(stream))
+    got, raised = [], None
+    try:
+        for row in samples:
+            got.append(row)
+    except Exception as e:  # noqa: BLE001
+        raised = type(e).__name__
+    assert raised == case["raises"]
+    assert got == case["samples"]

@@ -106,3 +106,20 @@ def test_live_reference_spot_check():
     ours = O.encode_stream(x, 44100, 16, 1000, max_lpc_order=10, qlp_precision=6, rice_min=1,
                            rice_max=3)
     assert b"".join(chunks) == ours
+
+
+@pytest.mark.parametrize("name", sorted(__import__("helpers").DECODE_CASES))
+def test_oracle_decodes_crafted_streams_like_the_reference(name):
+    """stream features the reference's encoder never produces (constant / verbatim subframes,
+    escaped partitions, 5-bit Rice method, wasted-bits flag, L/S, S/R, M/S, 3 channels, reserved
+    type, negative LPC shift): fixtures minted from the real reference decoder by
+    tests/golden/make_decode_golden.py"""
+    from helpers import DECODE_CASES, decode_case
+    case = DECODE_CASES[name]
+    stream, want = decode_case(case)
+    try:
+        pcm = O.decode_stream(stream)[4]
+        assert case["raises"] is None
+        assert pcm.shape == want.shape and (pcm == want).all()
+    except O.OracleError as e:
+        assert e.exc_class.__name__ == case["raises"]

@@ -170,3 +170,18 @@ def test_sim_decode_variable_block_sizes_take_the_unfiltered_path():
     rc, pcm, fch, _ = simlib.decode_frames(frames, 16)
     assert rc == 0 and pcm.shape == ref.shape and (pcm == ref).all()
     assert (pcm == np.concatenate([a, b])).all()
+
+
+@pytest.mark.parametrize("name", sorted(__import__("helpers").DECODE_CASES))
+def test_sim_decode_crafted_streams_like_the_reference(name):
+    """constant / verbatim subframes, escaped partitions, 5-bit Rice method, wasted-bits flag,
+    L/S, S/R, M/S, 3 channels, reserved type, negative LPC shift: the samples the reference
+    decoder yields, and the exception it ends with (fixtures from the real reference)"""
+    from helpers import DECODE_CASES, STATUS_NAMES, decode_case
+    case = DECODE_CASES[name]
+    stream, want = decode_case(case)
+    rc, pcm, fch, _ = simlib.decode_frames(stream[42:], 16)
+    assert STATUS_NAMES.get(rc, "?") == case["raises"]
+    assert pcm.shape[0] == want.shape[0]
+    if want.shape[0]:
+        assert pcm.shape == want.shape and (pcm == want).all()
