@@ -577,36 +577,15 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     /* Host buffers on both sides: cut the frame range into chunks and keep several in flight, so
      * that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap.
      * Chunks are whole waves of resident CTAs.  Everything else: one chunk. */
-    std::vector<u64> chunk_f0; /* first frame of every chunk, then n_frames */
-    chunk_f0.push_back(0);
+    std::vector<uint64_t> chunk_f0; /* first frame of every chunk, then n_frames */
     if (host_in && host_out && !info && !(flags & FLACB_SLOT_COMPACT)) {
-        const u64 wave = (u64)c->sm_count * (u64)plan.shape.ctas_per_sm;
-        u64 want = (16ull << 20) / (frame_pcm ? frame_pcm : 1);
-        want = (want + wave / 2) / wave * wave; /* whole waves of resident frames, nearest */
-        if (want < wave) want = wave;
-        /* one-wave kernels leave nothing to fill their tails with: two waves if that is still a
-         * small chunk (config 3: 13.1 vs 14.4 ms end to end; config 4's 98 MB would be too coarse) */
-        if (want < 2 * wave && 2 * wave * frame_pcm <= (32ull << 20)) want = 2 * wave;
-        u64 edge = wave;
-        if (const char *e = getenv("FLACB200_CHUNK_FRAMES")) { /* tuning / test knob: taken as it is */
-            want = (u64)atoll(e) > 0 ? (u64)atoll(e) : 1;
-            if (edge > want) edge = want;
-        }
-        if (want * 2 <= n_frames) {
-            /* the first and the last chunk are one wave: nothing overlaps the first chunk's input
-             * copy or the last chunk's kernels and output copy, so they are kept short */
-            u64 first = edge, last = edge;
-            if (const char *e = getenv("FLACB200_EDGE_CHUNK_FRAMES")) first = last = (u64)atoll(e) > 0 ? (u64)atoll(e) : want;
-            if (first + last >= n_frames) first = last = want;
-            u64 f = first < want ? first : want;
-            while (f + last < n_frames) {
-                chunk_f0.push_back(f);
-                f += want;
-            }
-            if (n_frames - chunk_f0.back() > last && last < want) chunk_f0.push_back(n_frames - last);
-        }
+        const char *e_want = getenv("FLACB200_CHUNK_FRAMES"), *e_edge = getenv("FLACB200_EDGE_CHUNK_FRAMES"); /* tuning / test knobs */
+        chunk_f0 = chunk_plan(n_frames, (u64)c->sm_count * (u64)plan.shape.ctas_per_sm, frame_pcm, e_want ? atoll(e_want) : 0,
+                              e_edge ? atoll(e_edge) : 0);
+    } else {
+        chunk_f0.push_back(0);
+        chunk_f0.push_back(n_frames);
     }
-    chunk_f0.push_back(n_frames);
     const u64 n_chunks = chunk_f0.size() - 1;
     float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f, stage_ms[4] = {0.f, 0.f, 0.f, 0.f};
     u64 host_off = 0; /* bytes produced so far */

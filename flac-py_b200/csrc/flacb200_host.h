@@ -168,6 +168,43 @@ inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t 
     return best;
 }
 
+/* Host path with host buffers on both sides: first frame of every chunk, then n_frames.  Chunks are
+ * whole waves of resident frames (`wave`), about 16 MB of PCM (two waves when that is still a
+ * small chunk: one-wave kernels leave nothing to fill their tails with); the first and the last
+ * chunk are one wave, because nothing overlaps the first chunk's input copy or the last chunk's
+ * kernels and output copy.  want_override > 0 (FLACB200_CHUNK_FRAMES): that many frames per
+ * chunk, taken as it is; edge_override > 0 (FLACB200_EDGE_CHUNK_FRAMES): size of the first and
+ * last chunk. */
+inline std::vector<uint64_t> chunk_plan(uint64_t n_frames, uint64_t wave, uint64_t frame_pcm, long long want_override,
+                                        long long edge_override)
+{
+    std::vector<uint64_t> f0;
+    f0.push_back(0);
+    if (wave < 1) wave = 1;
+    uint64_t want = (16ull << 20) / (frame_pcm ? frame_pcm : 1);
+    want = (want + wave / 2) / wave * wave; /* whole waves of resident frames, nearest */
+    if (want < wave) want = wave;
+    if (want < 2 * wave && 2 * wave * frame_pcm <= (32ull << 20)) want = 2 * wave;
+    uint64_t edge = wave;
+    if (want_override > 0) {
+        want = (uint64_t)want_override;
+        if (edge > want) edge = want;
+    }
+    if (want * 2 <= n_frames) {
+        uint64_t first = edge, last = edge;
+        if (edge_override > 0) first = last = (uint64_t)edge_override;
+        if (first + last >= n_frames) first = last = want;
+        uint64_t f = first < want ? first : want;
+        while (f + last < n_frames) {
+            f0.push_back(f);
+            f += want;
+        }
+        if (n_frames - f0.back() > last && last < want) f0.push_back(n_frames - last);
+    }
+    f0.push_back(n_frames);
+    return f0;
+}
+
 /* encoder.py:61-83, :170-189: magic, metadata block header (last, STREAMINFO, 34), STREAMINFO
  * with min = max block size, frame sizes 0, and a zero MD5 */
 inline void stream_prologue(uint32_t sample_rate, int channels, int bits, uint64_t total_samples,

@@ -154,3 +154,16 @@ def decode_frames(frames: bytes, streaminfo_bits: int, cap_samples: int | None =
                             out.ctypes.data, cap, C.byref(n), C.byref(fch), C.byref(nc))
     f = max(fch.value, 1)
     return rc, out[:n.value * f].reshape(-1, f).copy(), fch.value, nc.value
+
+
+def chunk_plan(n_frames: int, wave: int, frame_pcm: int, want: int = 0, edge: int = 0) -> list[int]:
+    """first frame of every chunk of the host path, then n_frames (flacb200_host.h chunk_plan)"""
+    L = lib()
+    L.flacb_sim_chunk_plan.restype = C.c_int
+    L.flacb_sim_chunk_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_longlong, C.c_longlong,
+                                       C.POINTER(C.c_uint64), C.c_int]
+    cap = int(n_frames) + 2
+    buf = (C.c_uint64 * cap)()
+    n = L.flacb_sim_chunk_plan(n_frames, wave, frame_pcm, want, edge, buf, cap)
+    assert n <= cap
+    return [int(buf[i]) for i in range(n)]

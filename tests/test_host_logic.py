@@ -168,3 +168,24 @@ def test_seektable_block_is_skipped_by_the_decoder_and_points_at_frames():
         sample, off, count = int.from_bytes(p[:8], "big"), int.from_bytes(p[8:16], "big"), int.from_bytes(p[16:], "big")
         assert sample == 3 * k * 1000 and enc.data[off:off + 2] == b"\xff\xf8"
         assert count == (1000 if 3 * k < 7 else 333)
+
+
+def test_chunk_plan_of_the_host_path():
+    """whole waves, about 16 MB, short first and last chunk; every frame in exactly one chunk"""
+    import simlib
+    # config 2: 18 KB frames, waves of 444 -> 888-frame chunks between one-wave edges
+    p = simlib.chunk_plan(5743, 444, 4608 * 2 * 2)
+    sizes = [b - a for a, b in zip(p[:-1], p[1:])]
+    assert p[0] == 0 and p[-1] == 5743 and sizes[0] == 444 and sizes[-1] == 444 and set(sizes[1:-2]) == {888}
+    # config 4: 110 KB frames: one wave is already 49 MB, chunks are not doubled
+    sizes = [b - a for a, b in zip(*(lambda q: (q[:-1], q[1:]))(simlib.chunk_plan(3125, 444, 4608 * 8 * 3)))]
+    assert set(sizes[:-1]) == {444} and sizes[-1] < 2 * 444
+    # config 3: waves of 148 big frames: two waves per chunk
+    sizes = [b - a for a, b in zip(*(lambda q: (q[:-1], q[1:]))(simlib.chunk_plan(3516, 148, 16384 * 2 * 3)))]
+    assert sizes[0] == 148 and sizes[-1] == 148 and 296 in sizes
+    for n in (1, 2, 71, 443, 444, 887, 888, 889, 1333, 5743, 100001):
+        for wave in (1, 148, 444):
+            for pcm in (64, 18432, 110592):
+                for want, edge in ((0, 0), (5, 0), (16, 0), (100000, 0), (888, 7)):
+                    q = simlib.chunk_plan(n, wave, pcm, want, edge)
+                    assert q[0] == 0 and q[-1] == n and all(b > a for a, b in zip(q[:-1], q[1:])), (n, wave, pcm, want, edge, q[:6])
