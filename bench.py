@@ -308,6 +308,32 @@ def main():
     barrier()
     assert e_len == flac_bytes
 
+    # ---- config 5 on the side (rank 0, stereo streams: the reference decoder's domain): decode the stream
+    # just produced, resident in HBM, back to PCM; checked against the input; not part of `value` ----
+    decode_info = None
+    if rank == 0 and ch == 2:
+        try:
+            pcm_cap = n * ch + 1024
+            d_pcm = ctx.device_alloc(pcm_cap * 4)
+            dms = []
+            for _ in range(4):
+                rc, nsf, fch, dst = ctx.decode_raw(d_out[(args.warmup + args.steps - 1) % copies], flac_bytes, bits,
+                                                   N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE, d_pcm, pcm_cap)
+                N.raise_for_status(rc, "decode (resident)")
+                dms.append(dst.kernel_ms)
+            head = np.empty(4096, dtype=np.int32)
+            ctx.d2h(head.ctypes.data, d_pcm, head.nbytes)
+            cb = (bits + 7) // 8
+            src = raw[:4096 * cb].reshape(-1, cb).astype(np.int32)
+            want = src[:, 0] | (src[:, 1] << 8) | ((src[:, 2] << 16) if cb == 3 else 0)
+            want = (want ^ (1 << (8 * cb - 1))) - (1 << (8 * cb - 1))
+            dk = float(np.median(dms[1:]))
+            decode_info = {"value": nsf * fch / dk / 1e3, "unit": "Msamples/s", "kernel_ms": dk, "sample_frames": int(nsf),
+                           "bit_exact_head": bool(nsf == n and fch == ch and (head == want).all()),
+                           "note": "BASELINE.json config 5 when the workload is c2: GPU decode of the stream encoded above, device resident"}
+        except Exception as e:  # noqa: BLE001  (never fail the encode bench over the side measurement)
+            decode_info = {"error": f"{type(e).__name__}: {e}"}
+
     # max over ranks of the device time; totals over ranks
     t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -357,7 +383,7 @@ def main():
                     "d2h_bytes_per_step": int(flac_bytes * world), "ms_per_step": e2e_ms / e2e_steps,
                     "h2d_ms": e_st.h2d_ms, "kernel_ms": e_st.kernel_ms, "d2h_ms": e_st.d2h_ms,
                     "realtime_x": e2e_value * 1e6 / (m["rate"] * ch)},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "decode": decode_info,
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_arm(args.workload, 0)
