@@ -17,6 +17,7 @@
 
 #include "flacb200_host.h"
 #include "flacb200_launch.h"
+#include "flacb200_serialise.cuh"
 #include "flacb200_decode.cuh"
 
 using namespace flacb;
@@ -106,6 +107,9 @@ struct flacb_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     int smem_optin = 0, sm_count = 0;
     size_t static_smem12 = 0, static_smem32 = 0;
+    size_t static2_fixed = 0, static2_12 = 0, static2_32 = 0; /* serialise_kernel */
+    DevBuf crc4, crc_w; /* slice-by-4 tables and x^(8 i) weights of the word-wise CRC-16 */
+    size_t crc_w_n = 0;
     EncSlot slot[FLACB_SLOTS];
     DevBuf win_full, win_tail;
     int win_full_n = -1, win_tail_n = -1;
@@ -183,6 +187,24 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     CUDA_TRY(init_fixed(tab, lo, hi.data()));
     CUDA_TRY(init_12(tab, lo, hi.data()));
     CUDA_TRY(init_32(tab, lo, hi.data()));
+    c->static2_fixed = static_smem2_fixed();
+    c->static2_12 = static_smem2_12();
+    c->static2_32 = static_smem2_32();
+    {
+        uint16_t t4[4][256];
+        crc16_slice4(t4);
+        int rc4 = c->crc4.ensure(sizeof(t4));
+        if (rc4) {
+            flacb_destroy(c);
+            return rc4;
+        }
+        cudaError_t e4 = cudaMemcpy(c->crc4.p, t4, sizeof(t4), cudaMemcpyHostToDevice);
+        if (e4 != cudaSuccess) {
+            g_cuda_error = cudaGetErrorString(e4);
+            flacb_destroy(c);
+            return FLACB_E_CUDA;
+        }
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = c;
     return FLACB_OK;
@@ -193,7 +215,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&c->win_full, &c->win_tail, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames, &c->d_dmisc, &c->d_recs};
+    DevBuf *bufs[] = {&c->win_full, &c->win_tail, &c->crc4, &c->crc_w, &c->d_stream, &c->d_pcm, &c->d_cand, &c->d_frames, &c->d_dmisc, &c->d_recs};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < FLACB_SLOTS; i++) {
         EncSlot &sl = c->slot[i];
@@ -317,7 +339,53 @@ struct EncPlan {
     bool staged;
     LaunchShape front;  /* shape of analyse_kernel */
     LaunchShape choose; /* shape of choose_kernel */
+    /* second-generation serialiser (flacb200_serialise.cuh) when the configuration is inside its limits */
+    bool ser2;
+    int ser_variant, ser_threads, ser_ctas;
+    SerLayout slay;
 };
+
+/* serialise_kernel: pick samples per thread / launch bounds (ser_variant) for the most resident
+ * threads per SM.  FLACB200_SERIALISE=1: the first-generation kernel; =2,<variant>[,<frames per SM>]:
+ * that variant (tuning / tests). */
+static void plan_serialise2(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
+{
+    plan.ser2 = false;
+    int forced = -1, forced_ctas = 0;
+    if (const char *e = getenv("FLACB200_SERIALISE")) {
+        if (atoi(e) == 1) return;
+        sscanf(e, "2,%d,%d", &forced, &forced_ctas);
+    }
+    if ((a.flags & FLACB_SLOT_COMPACT) || a.rice_max > V2_MAX_RICE) return;
+    const size_t st = a.max_lpc_order == 0 ? c->static2_fixed : a.max_lpc_order <= 12 ? c->static2_12 : c->static2_32;
+    static const int regs[4] = {72, 64, 112, 128};
+    int best_score = 0;
+    for (int v = 0; v < 4; v++) {
+        if (forced >= 0 && v != forced) continue;
+        const SerVariant sv = ser_variant(v);
+        const int S = 8 * sv.R;
+        int B = ((a.block_size + S - 1) / S + 31) / 32 * 32;
+        if (B > sv.max_threads) continue;
+        int ctas = 65536 / (regs[v] * B);
+        if (v == 0 && ctas > 3) ctas = 3; /* measured: more frames per SM than three did not pay */
+        if (ctas > 8) ctas = 8;
+        if (forced_ctas > 0 && ctas > forced_ctas) ctas = forced_ctas;
+        for (; ctas >= 1; ctas--) {
+            size_t per_cta = (size_t)(228 * 1024) / (size_t)ctas;
+            if (per_cta > (size_t)c->smem_optin + 1024) per_cta = (size_t)c->smem_optin + 1024;
+            if (per_cta <= st + 1024 + 4096) continue;
+            const SerLayout lay = make_ser_layout(a.block_size, a.channels, a.bits, a.rice_max, B, S, (uint32_t)(per_cta - st - 1024));
+            if (lay.stg_words == 0) continue;
+            const int score = ctas * B;
+            if (score > best_score) {
+                best_score = score;
+                plan.ser2 = true;
+                plan.ser_variant = v, plan.ser_threads = B, plan.ser_ctas = ctas, plan.slay = lay;
+            }
+            break;
+        }
+    }
+}
 
 /* "threads,all_planes,variant" tuning knobs */
 static void shape_from_env(const char *name, LaunchShape &sh, size_t static_smem, size_t smem_optin,
@@ -345,6 +413,7 @@ static int plan_encode(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
     if (plan.shape.threads == 0) return FLACB_E_UNSUPPORTED; /* the block does not fit shared memory */
     shape_from_env("FLACB200_SHAPE", plan.shape, plan.static_smem, (size_t)c->smem_optin, layout_total);
     plan.staged = a.max_lpc_order > 0;
+    plan_serialise2(c, a, plan);
     if (plan.staged) {
         /* stages A and C1: as many resident frames as the registers allow (three at 72), every
          * plane resident when that does not cost a frame */
@@ -465,7 +534,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     auto launch = [&](int kind, int variant, int threads, size_t smem, const EncParams &kp) {
         g_launches++;
         const unsigned grid = (unsigned)n_frames;
-        if (kind == K_FIXED) return launch_fixed(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
+        if (kind == K_FIXED || kind == K_FIXED2) return launch_fixed(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
         return plan.lmax12 ? launch_12(kind, variant, flavour, grid, threads, smem, sl.stream, kp)
                            : launch_32(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
     };
@@ -497,7 +566,14 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
         CUDA_TRY(cudaEventRecord(sl.ev_s[2], sl.stream));
     }
-    CUDA_TRY(launch(plan.staged ? K_SERIALISE : K_FIXED, shape.variant, B, lay.total, p));
+    if (plan.ser2) {
+        p.slay = plan.slay;
+        p.crc4 = (const uint16_t *)c->crc4.p;
+        p.crc_w = (const uint16_t *)c->crc_w.p;
+        CUDA_TRY(launch(plan.staged ? K_SERIALISE2 : K_FIXED2, plan.ser_variant, plan.ser_threads, plan.slay.total, p));
+    } else {
+        CUDA_TRY(launch(plan.staged ? K_SERIALISE : K_FIXED, shape.variant, B, lay.total, p));
+    }
     if (a.flags & FLACB_SLOT_COMPACT) {
         scan_frame_bytes_kernel<<<1, 256, 0, sl.stream>>>(p.frame_bytes, p.frame_off, p.n_frames);
         CUDA_TRY(cudaGetLastError());
@@ -512,8 +588,8 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     meta.h_frame_off = (u64 *)h;
     meta.h_stats = (u64 *)(h + (n_frames + 1) * 8);
     meta.h_status = (int32_t *)(h + (n_frames + 1) * 8 + 256);
-    meta.threads = B;
-    meta.smem = (int)lay.total;
+    meta.threads = plan.ser2 ? plan.ser_threads : B;
+    meta.smem = plan.ser2 ? (int)plan.slay.total : (int)lay.total;
     CUDA_TRY(cudaMemcpyAsync(meta.h_frame_off, sl.frame_off.p, (n_frames + 1) * 8, cudaMemcpyDeviceToHost, sl.stream));
     CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 256, cudaMemcpyDeviceToHost, sl.stream));
     CUDA_TRY(cudaMemcpyAsync(meta.h_status, sl.status.p, n_frames * 4, cudaMemcpyDeviceToHost, sl.stream));
@@ -572,6 +648,17 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
             (rc = upload_window(c, real_tail, c->win_tail, c->win_tail_n, c->win_tail_ok, c->flat_tail[0], c->flat_tail[1])))
             return rc;
     }
+    if (plan.ser2) { /* weights of the word-wise CRC-16: x^(8 i) for every distance to the end of a frame */
+        const size_t need = (size_t)frame_bound(block_size, channels, bits, rice_max) + 64;
+        if (c->crc_w_n < need) {
+            std::vector<uint16_t> w(need + need / 2);
+            crc16_weights(w.data(), w.size());
+            if ((rc = flacb_sync(c))) return rc; /* nothing in flight may still read the old table */
+            if ((rc = c->crc_w.ensure(w.size() * 2))) return rc;
+            CUDA_TRY(cudaMemcpy(c->crc_w.p, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+            c->crc_w_n = w.size();
+        }
+    }
     const bool host_in = !(flags & FLACB_INPUT_ON_DEVICE), host_out = !(flags & FLACB_OUTPUT_ON_DEVICE);
 
     /* Host buffers on both sides: cut the frame range into chunks and keep several in flight, so
@@ -580,7 +667,7 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
     std::vector<uint64_t> chunk_f0; /* first frame of every chunk, then n_frames */
     if (host_in && host_out && !info && !(flags & FLACB_SLOT_COMPACT)) {
         const char *e_want = getenv("FLACB200_CHUNK_FRAMES"), *e_edge = getenv("FLACB200_EDGE_CHUNK_FRAMES"); /* tuning / test knobs */
-        chunk_f0 = chunk_plan(n_frames, (u64)c->sm_count * (u64)plan.shape.ctas_per_sm, frame_pcm, e_want ? atoll(e_want) : 0,
+        chunk_f0 = chunk_plan(n_frames, (u64)c->sm_count * (u64)(plan.ser2 ? plan.ser_ctas : plan.shape.ctas_per_sm), frame_pcm, e_want ? atoll(e_want) : 0,
                               e_edge ? atoll(e_edge) : 0);
     } else {
         chunk_f0.push_back(0);

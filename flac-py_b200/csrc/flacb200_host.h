@@ -87,6 +87,32 @@ inline void crc16_xpow_tables(uint16_t lo[256], uint16_t *hi, int n_hi)
     }
 }
 
+/* slice-by-4 tables of the word-wise CRC-16: t[j][b] = b * x^(8 j + 16) mod 0x18005, so that
+ * four more message bytes w (big endian) take the CRC c to
+ * t[3][v >> 24] ^ t[2][(v >> 16) & 255] ^ t[1][(v >> 8) & 255] ^ t[0][v & 255], v = (c << 16) ^ w */
+inline void crc16_slice4(uint16_t t[4][256])
+{
+    crc16_table(t[0]);
+    for (int j = 1; j < 4; j++)
+        for (int b = 0; b < 256; b++) {
+            const uint32_t c = t[j - 1][b];
+            t[j][b] = (uint16_t)(((c << 8) ^ t[0][c >> 8]) & 0xFFFFu);
+        }
+}
+
+/* w[i] = x^(8 i) mod 0x18005: weight of a slice CRC with i bytes behind it */
+inline void crc16_weights(uint16_t *w, size_t n)
+{
+    uint32_t v = 1;
+    for (size_t i = 0; i < n; i++) {
+        w[i] = (uint16_t)v;
+        for (int k = 0; k < 8; k++) {
+            v <<= 1;
+            if (v & 0x10000u) v ^= 0x18005u;
+        }
+    }
+}
+
 /* Rice bits < N*(bps+3.01); plus parameters, warm-up, coefficients, headers */
 inline uint64_t frame_bound(int bs, int channels, int bps, int rice_max)
 {

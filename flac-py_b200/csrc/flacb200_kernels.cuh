@@ -215,6 +215,59 @@ __host__ __device__ inline SmemLayout make_layout_choose(int nmax, int channels,
     return l;
 }
 
+/* ---- shared memory plan of serialise_kernel (flacb200_serialise.cuh) ---- */
+constexpr int V2_GUARD = 32;   /* zero history in front of a plane (>= FLACB_MAX_LPC, a multiple of 32) */
+constexpr int V2_MAXC = 9;     /* candidate partition orders 0..8 */
+constexpr int V2_MAX_RICE = 8;
+
+/* plane index -> shared memory word: 16-byte units, eight to a 128-byte row, the unit index
+ * xor-ed with the row number.  Aligned groups of four words stay contiguous. */
+__host__ __device__ __forceinline__ uint32_t swz2(uint32_t i)
+{
+    const uint32_t u = i >> 2;
+    return ((u ^ ((u >> 3) & 7u)) << 2) | (i & 3u);
+}
+
+struct SerLayout {
+    uint32_t xwords;    /* words of one plane: guard + threads * S */
+    uint32_t pstride;   /* words between two planes: = 4 (mod 32), so that the same sample of two channels lies 4 banks apart */
+    uint32_t planes, kall, kall_stride, cumw, stg, stg_words, total;
+    int S;
+};
+
+/* worst-case bits of one subframe, SURVEY.md 9.5 (the per-channel part of frame_bound) */
+__host__ __device__ inline uint32_t subframe_bound_bytes(int bs, int bps, int rmax)
+{
+    return ((uint32_t)bs * (uint32_t)(bps + 4) + 7) / 8 + (1u << rmax) + 256;
+}
+
+/* budget: dynamic shared memory this frame may use.  stg_words == 0: does not fit. */
+__host__ __device__ inline SerLayout make_ser_layout(int nmax, int channels, int bps, int rmax, int threads, int S, uint32_t budget)
+{
+    SerLayout l;
+    l.S = S;
+    l.xwords = (uint32_t)(V2_GUARD + threads * S);
+    l.pstride = l.xwords + 4u;
+    uint32_t off = 0;
+    l.planes = off; off += align16(l.pstride * 4u * (uint32_t)channels);
+    l.kall_stride = align16(2u << rmax);
+    l.kall = off; off += l.kall_stride * (uint32_t)channels;
+    l.cumw = off; off += align16((uint32_t)threads * 8u);
+    l.stg = off;
+    const uint32_t per = subframe_bound_bytes(nmax, bps, rmax);
+    const uint32_t want = (per * (uint32_t)channels + 64 + 3) / 4 + 16; /* the whole frame */
+    const uint32_t least = (per + 3) / 4 + 32;                        /* one subframe + the partial word in front */
+    uint32_t words = 0;
+    if (budget >= off + 64) {
+        const uint32_t room = (budget - off - 32) / 4;
+        words = want <= room ? want : room;
+        if (words < least) words = 0;
+    }
+    l.stg_words = words;
+    l.total = off + align16((words + 4) * 4);
+    return l;
+}
+
 struct SubDecision;
 
 struct EncParams {
@@ -249,6 +302,10 @@ struct EncParams {
     uint8_t *pre;
     uint32_t pre_stride;
     SubDecision *dec;          /* [n_frames * channels] choices of choose_kernel for encode_frames_kernel<.., true> */
+    /* serialise_kernel (flacb200_serialise.cuh) */
+    SerLayout slay;
+    const uint16_t *crc4;      /* [4][256] slice-by-4 CRC-16 tables */
+    const uint16_t *crc_w;     /* x^(8 i) mod 0x18005 for i up to the frame bound */
 };
 
 #ifndef FLACB_HOST_ONLY

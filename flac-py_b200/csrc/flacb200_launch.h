@@ -16,8 +16,22 @@ enum KernelKind {
     K_FIXED = 0,     /* encode_frames_kernel<.., false>: fixed predictors only, one kernel       */
     K_ANALYSE = 1,   /* stage A : analyse_kernel                                                 */
     K_CHOOSE = 2,    /* stage C1: choose_kernel                                                  */
-    K_SERIALISE = 3  /* stage C2: encode_frames_kernel<.., true>                                 */
+    K_SERIALISE = 3, /* stage C2: encode_frames_kernel<.., true>                                 */
+    K_SERIALISE2 = 4,/* stage C2: serialise_kernel<.., true> (flacb200_serialise.cuh)            */
+    K_FIXED2 = 5     /* serialise_kernel<.., false>: fixed predictors only, one kernel           */
 };
+
+/* serialise_kernel variants: samples per thread S = 8 R and launch bounds */
+struct SerVariant { int R, max_threads, ctas; };
+inline SerVariant ser_variant(int v)
+{
+    switch (v) {
+    case 0: return {2, 288, 3};
+    case 1: return {2, 1024, 1};
+    case 2: return {1, 576, 1};
+    default: return {4, 512, 1};
+    }
+}
 
 /* variant 0: <576, 1> launch bounds, 1: <288, 3> (72 registers), 2: <288, 4> (56 registers, K_CHOOSE with
  * 288 threads only); flavour: lpc_errors_rolled's, K_CHOOSE only */
@@ -25,7 +39,8 @@ enum KernelKind {
     cudaError_t launch_##name(int kind, int variant, int flavour, unsigned grid, int threads, size_t smem,         \
                               cudaStream_t stream, const EncParams &p);                                            \
     cudaError_t init_##name(const uint16_t *crc_tab, const uint16_t *xpow_lo, const uint16_t *xpow_hi);            \
-    size_t static_smem_##name();
+    size_t static_smem_##name();                                                                                   \
+    size_t static_smem2_##name();
 FLACB_TU_DECL(fixed)
 FLACB_TU_DECL(12)
 FLACB_TU_DECL(32)

@@ -5,6 +5,7 @@
  */
 #define FLACB_TU_KERNELS_ONLY 1
 #include "flacb200_launch.h"
+#include "flacb200_serialise.cuh"
 
 namespace flacb {
 
@@ -67,9 +68,26 @@ cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour
 #endif
         return variant ? launch_one(encode_frames_kernel<LM, 288, 3, true, 0>, grid, threads, smem, stream, p)
                        : launch_one(encode_frames_kernel<LM, 576, 1, true, 0>, grid, threads, smem, stream, p);
+    case K_SERIALISE2: /* serialise_kernel<LMAX, chosen, R, launch bounds> */
+        switch (variant) {
+        case 0: return launch_one(serialise_kernel<LM, true, 2, 288, 3>, grid, threads, smem, stream, p);
+        case 1: return launch_one(serialise_kernel<LM, true, 2, 1024, 1>, grid, threads, smem, stream, p);
+        case 2: return launch_one(serialise_kernel<LM, true, 1, 576, 1>, grid, threads, smem, stream, p);
+        case 3: return launch_one(serialise_kernel<LM, true, 4, 512, 1>, grid, threads, smem, stream, p);
+        default: return cudaErrorInvalidValue;
+        }
     default: return cudaErrorInvalidValue;
     }
 #else
+    if (kind == K_FIXED2) {
+        switch (variant) {
+        case 0: return launch_one(serialise_kernel<4, false, 2, 288, 3>, grid, threads, smem, stream, p);
+        case 1: return launch_one(serialise_kernel<4, false, 2, 1024, 1>, grid, threads, smem, stream, p);
+        case 2: return launch_one(serialise_kernel<4, false, 1, 576, 1>, grid, threads, smem, stream, p);
+        case 3: return launch_one(serialise_kernel<4, false, 4, 512, 1>, grid, threads, smem, stream, p);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     if (kind != K_FIXED) return cudaErrorInvalidValue;
     if (variant && threads == 288) return launch_one(encode_frames_kernel<12, 288, 3, false, 288>, grid, threads, smem, stream, p);
     return variant ? launch_one(encode_frames_kernel<12, 288, 3, false, 0>, grid, threads, smem, stream, p)
@@ -93,6 +111,17 @@ size_t FLACB_CAT(static_smem_, FLACB_TU_NAME)()
     if (cudaFuncGetAttributes(&fa, encode_frames_kernel<FLACB_TU_LMAX, 576, 1, true, 0>) != cudaSuccess) return 8192;
 #else
     if (cudaFuncGetAttributes(&fa, encode_frames_kernel<12, 576, 1, false, 0>) != cudaSuccess) return 8192;
+#endif
+    return fa.sharedSizeBytes;
+}
+
+size_t FLACB_CAT(static_smem2_, FLACB_TU_NAME)()
+{
+    cudaFuncAttributes fa;
+#if FLACB_TU_LMAX
+    if (cudaFuncGetAttributes(&fa, serialise_kernel<FLACB_TU_LMAX, true, 2, 288, 3>) != cudaSuccess) return 12288;
+#else
+    if (cudaFuncGetAttributes(&fa, serialise_kernel<4, false, 2, 288, 3>) != cudaSuccess) return 12288;
 #endif
     return fa.sharedSizeBytes;
 }

@@ -31,6 +31,7 @@
 struct sim_dim3 { unsigned x, y, z; };
 struct double2 { double x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 struct int4 { int x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
 
@@ -222,6 +223,18 @@ template <class T> static inline T __reduce_add_sync(unsigned, T v)
     sim::syncwarp();
     T r = 0;
     for (int l = 0; l < 32; l++) r = (T)(r + (T)(long long)s.wbuf[w][l]);
+    sim::syncwarp();
+    return r;
+}
+template <class T> static inline T __reduce_min_sync(unsigned, T v)
+{
+    sim::State &s = sim::st();
+    const int w = s.cur >> 5, lane = s.cur & 31;
+    s.wbuf[w][lane] = (unsigned long long)v;
+    sim::syncwarp();
+    T r = v;
+    for (int l = 0; l < 32; l++)
+        if ((T)s.wbuf[w][l] < r) r = (T)s.wbuf[w][l];
     sim::syncwarp();
     return r;
 }

@@ -7,6 +7,7 @@
  * slow (a fiber per CUDA thread) and is never loaded by the product.
  */
 #define FLACB_CPU_SIM 1
+#include <stdio.h>
 #include "cpu_sim.h"
 
 namespace sim {
@@ -15,6 +16,7 @@ sim_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
 #include "../../flac-py_b200/csrc/flacb200_host.h"
 #include "../../flac-py_b200/csrc/flacb200_kernels.cuh"
+#include "../../flac-py_b200/csrc/flacb200_serialise.cuh"
 #include "../../flac-py_b200/csrc/flacb200_decode.cuh"
 
 using namespace flacb;
@@ -152,8 +154,51 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
             }
         }
     }
+    /* plane_mode bit 11: the second-generation serialiser (flacb200_serialise.cuh); bits 12-13:
+     * samples per thread (0: 16, 1: 8, 2: 32); bit 14: a small staging window (mid-frame flushes) */
+    const bool ser2 = (plane_mode & 0x800u) != 0;
+    uint16_t crc4[4][256];
+    std::vector<uint16_t> crc_w;
+    if (ser2) {
+        if (rice_max > V2_MAX_RICE || (flags & FLACB_SLOT_COMPACT)) return FLACB_E_UNSUPPORTED;
+        const int rsel = (int)((plane_mode >> 12) & 3u);
+        const int R = rsel == 1 ? 1 : rsel == 2 ? 4 : 2;
+        const int S = 8 * R;
+        int Bt = ((block_size + S - 1) / S + 31) / 32 * 32;
+        if (threads_override) Bt = threads_override;
+        if (Bt > 1024 || Bt * S < block_size) return FLACB_E_UNSUPPORTED;
+        uint32_t budget = 220 * 1024;
+        if (plane_mode & 0x4000u) {
+            const SerLayout probe = make_ser_layout(block_size, channels, bits, rice_max, Bt, S, 220 * 1024);
+            budget = probe.stg + (((subframe_bound_bytes(block_size, bits, rice_max) + 3) / 4 + 32) + 8) * 4 + 64;
+        }
+        p.slay = make_ser_layout(block_size, channels, bits, rice_max, Bt, S, budget);
+        if (p.slay.stg_words == 0) return FLACB_E_UNSUPPORTED;
+        if (getenv("FLACB_SIM_TRACE")) fprintf(stderr, "ser2: Bt %d S %d stg_words %u total %u\n", Bt, S, p.slay.stg_words, p.slay.total);
+        crc16_slice4(crc4);
+        crc_w.resize(frame_bound(block_size, channels, bits, rice_max) + 64);
+        crc16_weights(crc_w.data(), crc_w.size());
+        p.crc4 = &crc4[0][0];
+        p.crc_w = crc_w.data();
+        if (getenv("FLACB_SIM_TRACE")) fprintf(stderr, "ser2: tables built\n");
+        for (uint64_t f = 0; f < n_frames; f++) {
+            const unsigned fu = (unsigned)f, g = (unsigned)n_frames;
+            const size_t dyn2 = p.slay.total;
+#define SER_RUN(LM, CH)                                                                                         \
+    do {                                                                                                        \
+        if (R == 1) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 1, 1024, 1>(p); });       \
+        else if (R == 2) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 2, 1024, 1>(p); });  \
+        else sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 4, 1024, 1>(p); });              \
+    } while (0)
+            if (!staged) SER_RUN(4, false);
+            else if (max_lpc_order <= 12) SER_RUN(12, true);
+            else SER_RUN(32, true);
+#undef SER_RUN
+            if (getenv("FLACB_SIM_TRACE")) fprintf(stderr, "ser2: frame %u done\n", fu);
+        }
+    }
     const size_t dyn = p.lay.total;
-    for (uint64_t f = 0; f < n_frames; f++) {
+    for (uint64_t f = 0; f < n_frames && !ser2; f++) {
         if (!staged)
             sim::run_block((unsigned)f, (unsigned)n_frames, B, dyn, [&]() { encode_frames_kernel<12, 576, 1, false, 0>(p); });
         else if (max_lpc_order <= 12)

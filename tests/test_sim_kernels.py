@@ -185,3 +185,67 @@ def test_sim_decode_crafted_streams_like_the_reference(name):
     assert pcm.shape[0] == want.shape[0]
     if want.shape[0]:
         assert pcm.shape == want.shape and (pcm == want).all()
+
+
+# ---- second-generation serialiser (flacb200_serialise.cuh): plane_mode bit 11; bits 12-13 pick the
+# samples per thread (16 / 8 / 32), bit 14 a staging window of one worst-case subframe (mid-frame flushes)
+SER2 = 0x800
+SER2_MODES = {"s16": SER2, "s8": SER2 | 0x1000, "s32": SER2 | 0x2000, "s16_smallwin": SER2 | 0x4000}
+
+
+@pytest.mark.parametrize("mode", sorted(SER2_MODES))
+@pytest.mark.parametrize("name", FAST + ["many_frames"])
+def test_sim_serialise_kernel_matches_golden(name, mode):
+    case = CASES[name]
+    if mode == "s8" and case["block_size"] > 8 * 1024:
+        pytest.skip("8 samples per thread: blocks up to 8192")
+    x = case_pcm(case)
+    rc, data, offs, _, st = simlib.encode_frames(x, case["bits"], plane_mode=SER2_MODES[mode], **case_kwargs(case))
+    assert rc == 0
+    assert data == case_stream(case)[42:]
+    lens = [4, 4, 34] + [int(b - a) for a, b in zip(offs[:-1], offs[1:])]
+    assert lens == case["chunk_lengths"]
+
+
+@pytest.mark.parametrize("ch,bits,L,q,bs,cls", SHAPES + [(2, 16, 0, 5, 1000, "mixed"), (1, 24, 0, 5, 333, "white"), (7, 8, 6, 6, 96, "white")])
+def test_sim_serialise_kernel_other_shapes_against_the_oracle(ch, bits, L, q, bs, cls):
+    """channel counts without a vector load path, odd block sizes (partitions that are not a multiple of
+    a thread's span, unaligned frame starts), fixed predictors only, 8-bit samples"""
+    import flacb200_synth as S
+    x = S.pcm(bs * 3 + bs // 3 + 5, ch, bits, 48000, cls, 99 + ch + bits)
+    ref = O.encode_frames(x, bits, bs, L, q, 0, 4)
+    for mode in (SER2, SER2 | 0x1000, SER2 | 0x4000):
+        rc, data, offs, info, st = simlib.encode_frames(x, bits, bs, L, q, 0, 4, plane_mode=mode, want_info=True)
+        assert rc == 0 and data == ref.data and (offs == ref.frame_offsets).all(), hex(mode)
+        rc1, data1, _, info1, _ = simlib.encode_frames(x, bits, bs, L, q, 0, 4, want_info=True)
+        for a, b in zip(info, info1):  # the introspection records of both serialisers agree
+            assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("name", sorted(OOD))
+def test_sim_serialise_kernel_out_of_domain_statuses(name):
+    """same status, same first bad frame and, in lenient mode, same bytes as the first-generation kernel"""
+    case = OOD[name]
+    x = ood_pcm(case)
+    kw = {k: case[k] for k in ("block_size", "max_lpc_order", "qlp_precision", "rice_min", "rice_max")}
+    for flags in (0, simlib.FLAG_LENIENT):
+        a = simlib.encode_frames(x, case["bits"], flags=flags, **kw)
+        b = simlib.encode_frames(x, case["bits"], flags=flags, plane_mode=SER2, **kw)
+        assert a[0] == b[0] and a[1] == b[1] and (a[2] == b[2]).all()
+        assert a[4].first_bad_frame == b[4].first_bad_frame and a[4].out_of_domain == b[4].out_of_domain
+
+
+def test_sim_serialise_kernel_partial_threads_and_rice_min():
+    """more threads than spans (idle threads behind the block), rice_min > 0 with an odd block (no admissible order)"""
+    import flacb200_synth as S
+    x = S.pcm(2304 * 2 + 77, 2, 16, 44100, "mixed", 5)
+    rc, data, offs, _, _ = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6, plane_mode=SER2, threads=192)
+    old = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6)
+    assert rc == old[0] == 1 and data == old[1]  # the 77-sample tail has no admissible order >= 1: AssertionError
+    with pytest.raises(O.OracleError):
+        O.encode_frames(x, 16, 2304, 8, 7, 1, 6)
+    full = x[:2304 * 2]
+    assert simlib.encode_frames(full, 16, 2304, 8, 7, 1, 6, plane_mode=SER2, threads=192)[1] == O.encode_frames(full, 16, 2304, 8, 7, 1, 6).data
+    a = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6, flags=simlib.FLAG_LENIENT)
+    b = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6, flags=simlib.FLAG_LENIENT, plane_mode=SER2, threads=192)
+    assert a[0] == b[0] and a[1] == b[1]
