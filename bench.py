@@ -161,21 +161,100 @@ def cpu_arm(name: str, rank: int, target_s: float = 15.0, threads: int | None = 
     cores = threads or os.cpu_count() or 1
     probe = S.pcm(bs * cores, ch, bits, rate, "mixed", seed)
     t0 = time.perf_counter()
-    O.encode_frames(probe, bits, bs, L, q, rmin, rmax, threads=cores)
+    oracle_in_domain(probe, bits, bs, L, q, rmin, rmax, threads=cores)
     per_round = max(time.perf_counter() - t0, 1e-4)
     rounds = int(max(1, min(target_s / per_round, (rate * secs) // (bs * cores))))
     x = S.pcm(bs * cores * rounds, ch, bits, rate, "mixed", seed)
     dt, passes = 0.0, 0
+    nfr_ok = cores * rounds
     while dt < target_s * 0.6 or passes == 0:  # repeat the slice until enough CPU time is on the clock
         t0 = time.perf_counter()
-        enc = O.encode_frames(x, bits, bs, L, q, rmin, rmax, threads=cores)
+        enc, nfr_ok = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, threads=cores)
         dt += time.perf_counter() - t0
         passes += 1
     ms = x.shape[0] * ch * passes / dt / 1e6
-    return {"value": ms, "unit": "Msamples/s", "cores": cores, "kind": "port",
+    return {"value": ms, "unit": "Msamples/s", "cores": cores, "kind": "port", "_enc": enc, "_frames": nfr_ok,
             "sample": f"first {x.shape[0]} sample frames ({cores * rounds} frames, {x.shape[0] / rate:.1f} s of audio) of the "
                       f"workload, {passes} passes, oracle/flac_oracle.c with {cores} threads, {dt:.2f} s wall, {len(enc.data)} bytes out per pass",
             "seconds": dt, "realtime_x": x.shape[0] * passes / rate / dt}
+
+
+def oracle_in_domain(x, bits, bs, L, q, rmin, rmax, **kw):
+    """Oracle encode of the frames in front of the first one the reference raises on (the oracle has no
+    lenient mode: parity is only defined inside the reference's domain)."""
+    import oracle as O
+    try:
+        return O.encode_frames(x, bits, bs, L, q, rmin, rmax, **kw), (x.shape[0] + bs - 1) // bs
+    except O.OracleError as e:
+        k = max(int(e.frame), 0)
+        return O.encode_frames(x[:k * bs], bits, bs, L, q, rmin, rmax, **kw), k
+
+
+def parity_check(ctx, N, name: str, rank: int, raw: np.ndarray, m: dict, d_in: int, d_out: int, cap: int, enc_args: tuple,
+                 oracle_enc=None, oracle_frames: int = 0, info_frames: int = 48) -> dict:
+    """The stream this rank's GPU produced against the CPU oracle, on the same PCM:
+    * bytes of the first `oracle_frames` frames (the slice the CPU arm encoded anyway; a smaller slice
+      is encoded here when there is none, i.e. on ranks > 0 and with --no-cpu-baseline);
+    * per subframe of the first `info_frames` frames: autocorrelation lags (bit patterns), quantised
+      coefficients + shifts of every order, the decisions (type, order, partition order, parameters).
+    north_star: "identical quantized coefficients wherever the fp64 autocorrelation agrees, and report a
+    mismatch rate otherwise" -- coefficient sets are only compared where every lag agrees."""
+    import oracle as O
+    import flacb200_synth as S
+    desc, ch, bits, rate, secs, bs, L, q, rmin, rmax, seed = WORKLOADS[name]
+    n = m["n"]
+    nfr = (n + bs - 1) // bs
+    offs = np.zeros(nfr + 1, dtype=np.uint64)
+    flags = N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT
+    rc, out_len, st = ctx.encode_raw(d_in, *enc_args, flags, d_out, cap, frame_offsets=offs)
+    N.raise_for_status(rc, "encode (parity)")
+    if oracle_enc is None or rank != 0:
+        oracle_frames = min(nfr, 64)
+        x = S.pcm(min(n, bs * oracle_frames), ch, bits, rate, "mixed", seed, start=rank * n)
+        oracle_enc, oracle_frames = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=rank * nfr,
+                                                     threads=os.cpu_count() or 1)
+    k = min(oracle_frames, nfr)
+    want = np.frombuffer(oracle_enc.data, dtype=np.uint8)[:int(oracle_enc.frame_offsets[k])]
+    got = np.empty(int(offs[k]), dtype=np.uint8)
+    if got.size:
+        ctx.d2h(got.ctypes.data, d_out, got.size)
+    mlen = min(got.size, want.size)
+    byte_mismatches = int(np.count_nonzero(got[:mlen] != want[:mlen])) + abs(got.size - want.size)
+    frame_mismatches = int(np.count_nonzero(offs[:k + 1] != oracle_enc.frame_offsets[:k + 1]))
+    out = {"frames_checked": int(k), "bytes_checked": int(want.size), "byte_mismatches": byte_mismatches,
+           "frame_offset_mismatches": frame_mismatches}
+    # stage values on a slice (needs the per-subframe records: a separate small encode on both sides)
+    kf = min(info_frames, nfr)
+    ns = min(n, kf * bs)
+    if L > 0 and kf > 0:
+        x = S.pcm(ns, ch, bits, rate, "mixed", seed, start=rank * n)
+        ref, kf = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=rank * nfr, want_info=True)
+        ns = min(ns, kf * bs)
+        info = (N.SubframeInfo * max(kf * ch, 1))()
+        if kf:
+            rc, _, _ = ctx.encode_raw(d_in, ns, *enc_args[1:], flags, d_out, cap, info=info)
+            N.raise_for_status(rc, "encode (parity, stage values)")
+        lags = lag_bad = sets = set_bad = dec_bad = 0
+        for a, r in zip(list(info)[:kf * ch], ref.info or []):
+            la = [a.autoc[i] for i in range(L + 1)]
+            lr = [r.autoc[i] for i in range(L + 1)]
+            bad = sum(1 for u, v in zip(la, lr) if np.float64(u).tobytes() != np.float64(v).tobytes())
+            lags += L + 1
+            lag_bad += bad
+            if bad == 0:
+                for o in range(L):
+                    sets += 1
+                    if (a.lpc_ncoef[o] != r.lpc_ncoef[o] or a.lpc_shift[o] != r.lpc_shift[o]
+                            or list(a.lpc_q[o][:a.lpc_ncoef[o]]) != list(r.lpc_q[o][:r.lpc_ncoef[o]])):
+                        set_bad += 1
+            if (a.type, a.order, a.porder, a.method, a.bits) != (r.type, r.order, r.porder, r.method, r.bits):
+                dec_bad += 1
+        out.update({"subframes_checked": int(kf * ch), "lpc_lags_checked": lags, "lpc_lag_mismatches": lag_bad,
+                    "lpc_coef_sets_checked": sets, "lpc_coef_mismatches": set_bad, "decision_mismatches": dec_bad,
+                    "lpc_lag_mismatch_rate": lag_bad / lags if lags else 0.0})
+    else:
+        out.update({"subframes_checked": 0, "lpc_lag_mismatches": 0, "lpc_coef_mismatches": 0, "decision_mismatches": 0})
+    return out
 
 
 def main():
@@ -308,29 +387,100 @@ def main():
     barrier()
     assert e_len == flac_bytes
 
+    # ---- the CPU arm (rank 0, one GPU): the oracle port on a bounded slice of the same PCM; its bytes are
+    # the reference for the parity check below ----
+    cb_arm = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb_arm = cpu_arm(args.workload, 0)
+
+    # ---- parity of the benchmarked stream itself (every rank checks its own frame range) ----
+    last = (args.warmup + args.steps - 1) % copies
+    try:
+        parity = parity_check(ctx, N, args.workload, rank, raw, m, d_in[last], d_out[last], cap, enc_args,
+                              cb_arm["_enc"] if cb_arm else None, cb_arm["_frames"] if cb_arm else 0)
+    except Exception as e:  # noqa: BLE001
+        parity = {"error": f"{type(e).__name__}: {e}"}
+    shard_check = None
+    if world > 1:
+        import hashlib
+        mine = np.empty(flac_bytes, dtype=np.uint8)
+        ctx.d2h(mine.ctypes.data, d_out[last], flac_bytes)
+        digests = [None] * world
+        dist.all_gather_object(digests, (int(flac_bytes), hashlib.sha256(mine.tobytes()).hexdigest(),
+                                         {k: v for k, v in parity.items() if isinstance(v, (int, float))}))
+        if rank == 0:
+            # rank 0 encodes the last rank's frame range on its own GPU: a sharded encode must give the bytes a
+            # single GPU gives for that range (frame numbers included), so the ranks' streams concatenate to the
+            # single stream
+            r = world - 1
+            raw_r, _ = synth(args.workload, r, args.seconds)
+            pin_in.array[:] = raw_r
+            ctx.h2d(d_in[0], pin_in.ptr, pcm_bytes)
+            rc, len_r, _ = ctx.encode_raw(d_in[0], *enc_args[:-1], r * nfr, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT, d_out[0], cap)
+            N.raise_for_status(rc, "encode (shard check)")
+            other = np.empty(len_r, dtype=np.uint8)
+            ctx.d2h(other.ctypes.data, d_out[0], len_r)
+            shard_check = {"rank_reencoded_on_rank0": r, "bytes": int(len_r),
+                           "identical": bool(len_r == digests[r][0] and hashlib.sha256(other.tobytes()).hexdigest() == digests[r][1]),
+                           "stream_bytes_per_rank": [d[0] for d in digests]}
+            tot = {}
+            for d in digests:
+                for k, v in d[2].items():
+                    if k != "lpc_lag_mismatch_rate":
+                        tot[k] = tot.get(k, 0) + v
+            if tot.get("lpc_lags_checked"):
+                tot["lpc_lag_mismatch_rate"] = tot["lpc_lag_mismatches"] / tot["lpc_lags_checked"]
+            parity = tot | {"ranks": world}
+
     # ---- config 5 on the side (rank 0, stereo streams: the reference decoder's domain): decode the stream
-    # just produced, resident in HBM, back to PCM; checked against the input; not part of `value` ----
+    # just produced back to PCM; the WHOLE result is compared with the input; not part of `value` ----
     decode_info = None
     if rank == 0 and ch == 2:
         try:
+            import oracle as O
             pcm_cap = n * ch + 1024
             d_pcm = ctx.device_alloc(pcm_cap * 4)
             dms = []
             for _ in range(4):
-                rc, nsf, fch, dst = ctx.decode_raw(d_out[(args.warmup + args.steps - 1) % copies], flac_bytes, bits,
-                                                   N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE, d_pcm, pcm_cap)
+                rc, nsf, fch, dst = ctx.decode_raw(d_out[last], flac_bytes, bits, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE, d_pcm, pcm_cap)
                 N.raise_for_status(rc, "decode (resident)")
                 dms.append(dst.kernel_ms)
-            head = np.empty(4096, dtype=np.int32)
-            ctx.d2h(head.ctypes.data, d_pcm, head.nbytes)
-            cb = (bits + 7) // 8
-            src = raw[:4096 * cb].reshape(-1, cb).astype(np.int32)
-            want = src[:, 0] | (src[:, 1] << 8) | ((src[:, 2] << 16) if cb == 3 else 0)
-            want = (want ^ (1 << (8 * cb - 1))) - (1 << (8 * cb - 1))
+            cbytes = (bits + 7) // 8
+            src = raw.reshape(-1, cbytes).astype(np.int32)
+            want = src[:, 0] | (src[:, 1] << 8) | ((src[:, 2] << 16) if cbytes == 3 else 0)
+            want = (want ^ (1 << (8 * cbytes - 1))) - (1 << (8 * cbytes - 1))
+            # end to end: stream in pinned host memory -> interleaved int32 PCM in pinned host memory
+            pin_pcm = N.PinnedBuffer(pcm_cap * 4)
+            ctx.d2h(pin_out.ptr, d_out[last], flac_bytes)
+            e_ms = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                rc, nsf2, fch2, dst2 = ctx.decode_raw(pin_out.ptr, flac_bytes, bits, 0, pin_pcm.ptr, pcm_cap)
+                e_ms.append((time.perf_counter() - t0) * 1e3)
+                N.raise_for_status(rc, "decode (host buffers)")
+            got = pin_pcm.array.view(np.int32)[:nsf2 * fch2]
+            exact = bool(nsf2 == n and fch2 == ch and got.size == want.size and (got == want).all())
             dk = float(np.median(dms[1:]))
+            de = float(np.median(e_ms[1:]))
+            # CPU arm of the decode: the oracle's decoder (one thread, like the reference) on the first frames
+            k = min(nfr, 256)
+            offs = np.zeros(nfr + 1, dtype=np.uint64)
+            rc, _, _ = ctx.encode_raw(d_in[last], *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT, d_out[last], cap, frame_offsets=offs)
+            head_stream = O.stream_prologue(m["rate"], ch, bits, k * bs, bs) + pin_out.array[:int(offs[k])].tobytes()
+            t0 = time.perf_counter()
+            dec = O.decode_stream(head_stream)
+            cpu_s = time.perf_counter() - t0
+            algo_d = flac_bytes + n * ch * cbytes
             decode_info = {"value": nsf * fch / dk / 1e3, "unit": "Msamples/s", "kernel_ms": dk, "sample_frames": int(nsf),
-                           "bit_exact_head": bool(nsf == n and fch == ch and (head == want).all()),
-                           "note": "BASELINE.json config 5 when the workload is c2: GPU decode of the stream encoded above, device resident"}
+                           "bit_exact": exact, "samples_compared": int(want.size),
+                           "e2e": {"value": nsf2 * fch2 / de / 1e3, "unit": "Msamples/s", "ms": de, "h2d_bytes": int(flac_bytes),
+                                   "d2h_bytes": int(nsf2 * fch2 * 4), "h2d_ms": dst2.h2d_ms, "d2h_ms": dst2.d2h_ms},
+                           "roofline": {"bound": "hbm", "achieved": algo_d / dk / 1e6, "peak": peak_hbm()[0], "unit": "GB/s",
+                                        "frac": algo_d / dk / 1e6 / peak_hbm()[0], "algorithmic_bytes": int(algo_d)},
+                           "cpu_baseline": {"value": k * bs * ch / cpu_s / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                            "sample": f"first {k} frames of the stream, oracle/flac_oracle.c decoder, one thread, {cpu_s:.2f} s",
+                                            "bit_exact": bool((np.asarray(dec[4]).reshape(-1) == want[:k * bs * ch]).all())},
+                           "note": "BASELINE.json config 5 when the workload is c2: GPU decode of the stream encoded above"}
         except Exception as e:  # noqa: BLE001  (never fail the encode bench over the side measurement)
             decode_info = {"error": f"{type(e).__name__}: {e}"}
 
@@ -383,13 +533,11 @@ def main():
                     "d2h_bytes_per_step": int(flac_bytes * world), "ms_per_step": e2e_ms / e2e_steps,
                     "h2d_ms": e_st.h2d_ms, "kernel_ms": e_st.kernel_ms, "d2h_ms": e_st.d2h_ms,
                     "realtime_x": e2e_value * 1e6 / (m["rate"] * ch)},
-            "gpu_launches": int(launches), "clocks": clocks, "decode": decode_info,
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "decode": decode_info,
         }
-        if not args.no_cpu_baseline and world == 1:
-            cb = cpu_arm(args.workload, 0)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        else:
-            line["cpu_baseline"] = None
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        line["cpu_baseline"] = {k: cb_arm[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb_arm else None
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

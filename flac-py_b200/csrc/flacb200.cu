@@ -118,6 +118,14 @@ struct flacb_ctx {
     /* decode */
     DevBuf d_stream, d_pcm, d_cand, d_frames, d_dmisc, d_recs;
     HostBuf h_dmeta;
+    cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr; /* decode: output copy */
+    /* a decode whose output did not fit the caller's buffer: flacb_decode_output finishes it */
+    struct {
+        bool valid = false;
+        u64 n_cand = 0, total = 0, nsf = 0, n_frames = 0;
+        int fch = 0, status = 0;
+        float k_ms = 0.f, h2d_ms = 0.f;
+    } pend_dec;
 };
 
 extern "C" int flacb_version(void) { return FLACB_VERSION; }
@@ -147,6 +155,8 @@ extern "C" int flacb_stream_prologue(uint32_t sample_rate, int channels, int bit
     return FLACB_OK;
 }
 
+static int create_impl(flacb_ctx *c, int device);
+
 extern "C" int flacb_create(int device, flacb_ctx **out)
 {
     if (!out) return FLACB_E_ASSERT;
@@ -160,11 +170,24 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
     CUDA_TRY(cudaSetDevice(device));
     flacb_ctx *c = new flacb_ctx();
     c->device = device;
+    const int rc = create_impl(c, device);
+    if (rc != FLACB_OK) {
+        const std::string why = g_cuda_error; /* flacb_destroy may overwrite it */
+        flacb_destroy(c); /* streams, events and buffers made so far */
+        g_cuda_error = why;
+        return rc;
+    }
+    *out = c;
+    return FLACB_OK;
+}
+
+static int create_impl(flacb_ctx *c, int device)
+{
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-    cudaEvent_t *evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_t0, &c->ev_t1, &c->ev_c0, &c->ev_c1};
+    cudaEvent_t *evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_t0, &c->ev_t1, &c->ev_c0, &c->ev_c1, &c->ev_d0, &c->ev_d1};
     for (cudaEvent_t *e : evs) CUDA_TRY(cudaEventCreate(e));
     for (int i = 0; i < FLACB_SLOTS; i++) {
         EncSlot &sl = c->slot[i];
@@ -194,19 +217,10 @@ extern "C" int flacb_create(int device, flacb_ctx **out)
         uint16_t t4[4][256];
         crc16_slice4(t4);
         int rc4 = c->crc4.ensure(sizeof(t4));
-        if (rc4) {
-            flacb_destroy(c);
-            return rc4;
-        }
-        cudaError_t e4 = cudaMemcpy(c->crc4.p, t4, sizeof(t4), cudaMemcpyHostToDevice);
-        if (e4 != cudaSuccess) {
-            g_cuda_error = cudaGetErrorString(e4);
-            flacb_destroy(c);
-            return FLACB_E_CUDA;
-        }
+        if (rc4) return rc4;
+        CUDA_TRY(cudaMemcpy(c->crc4.p, t4, sizeof(t4), cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaDeviceSynchronize());
-    *out = c;
     return FLACB_OK;
 }
 
@@ -228,7 +242,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
         if (i > 0 && sl.stream) cudaStreamDestroy(sl.stream);
     }
     c->h_dmeta.release();
-    cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_t0, c->ev_t1, c->ev_c0, c->ev_c1};
+    cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_t0, c->ev_t1, c->ev_c0, c->ev_c1, c->ev_d0, c->ev_d1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -358,16 +372,15 @@ static void plan_serialise2(flacb_ctx *c, const EncodeArgs &a, EncPlan &plan)
     }
     if ((a.flags & FLACB_SLOT_COMPACT) || a.rice_max > V2_MAX_RICE) return;
     const size_t st = a.max_lpc_order == 0 ? c->static2_fixed : a.max_lpc_order <= 12 ? c->static2_12 : c->static2_32;
-    static const int regs[4] = {72, 64, 112, 128};
     int best_score = 0;
-    for (int v = 0; v < 4; v++) {
+    for (int v = 0; v < SER_VARIANTS; v++) {
         if (forced >= 0 && v != forced) continue;
         const SerVariant sv = ser_variant(v);
-        const int S = 8 * sv.R;
+        const int S = sv.S;
         int B = ((a.block_size + S - 1) / S + 31) / 32 * 32;
         if (B > sv.max_threads) continue;
-        int ctas = 65536 / (regs[v] * B);
-        if (v == 0 && ctas > 3) ctas = 3; /* measured: more frames per SM than three did not pay */
+        int ctas = 65536 / (sv.regs * B);
+        if (ctas > sv.ctas && sv.ctas > 1) ctas = sv.ctas; /* measured: more frames per SM than three did not pay */
         if (ctas > 8) ctas = 8;
         if (forced_ctas > 0 && ctas > forced_ctas) ctas = forced_ctas;
         for (; ctas >= 1; ctas--) {
@@ -613,11 +626,41 @@ static int first_bad(const ChunkMeta &meta, u64 n_frames, uint32_t flags, int64_
     return FLACB_OK;
 }
 
+static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_frames, int channels, int bits,
+                           int block_size, int max_lpc_order, int qlp_precision, int rice_min, int rice_max,
+                           uint64_t first_frame_number, uint32_t flags, uint8_t *out, uint64_t out_cap,
+                           uint64_t *out_len, uint64_t *frame_offsets, flacb_subframe_info *info,
+                           flacb_stats *stats);
+
 extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample_frames, int channels, int bits,
                                 int block_size, int max_lpc_order, int qlp_precision, int rice_min, int rice_max,
                                 uint64_t first_frame_number, uint32_t flags, uint8_t *out, uint64_t out_cap,
                                 uint64_t *out_len, uint64_t *frame_offsets, flacb_subframe_info *info,
                                 flacb_stats *stats)
+{
+    const int rc = encode_pcm_impl(c, pcm, n_sample_frames, channels, bits, block_size, max_lpc_order, qlp_precision, rice_min,
+                                   rice_max, first_frame_number, flags, out, out_cap, out_len, frame_offsets, info, stats);
+    if (c && rc != FLACB_OK) {
+        /* An early exit (a failed allocation, launch or copy, or the first frame the reference raises on)
+         * can leave kernels and copies of other chunks in flight that still write into the caller's
+         * buffers: wait for all of them before the buffers go back to the caller, and forget them. */
+        cudaSetDevice(c->device);
+        for (int i = 0; i < FLACB_SLOTS; i++) {
+            cudaStreamSynchronize(c->slot[i].stream);
+            c->slot[i].d2h_pending = false;
+        }
+        cudaStreamSynchronize(c->h2d_stream);
+        cudaStreamSynchronize(c->d2h_stream);
+        if (rc == FLACB_E_CUDA) cudaGetLastError(); /* the text is in flacb_last_cuda_error() */
+    }
+    return rc;
+}
+
+static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_frames, int channels, int bits,
+                           int block_size, int max_lpc_order, int qlp_precision, int rice_min, int rice_max,
+                           uint64_t first_frame_number, uint32_t flags, uint8_t *out, uint64_t out_cap,
+                           uint64_t *out_len, uint64_t *frame_offsets, flacb_subframe_info *info,
+                           flacb_stats *stats)
 {
     if (out_len) *out_len = 0;
     if (stats) {
@@ -731,10 +774,11 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
 #ifdef FLACB_PHASE_TIMING
         {
             u64 tot = 0;
-            for (int k = 0; k < 12; k++) tot += pd.meta.h_stats[8 + k];
-            fprintf(stderr, "phase cycles %%:");
-            for (int k = 0; k < 12; k++) fprintf(stderr, " %d:%.1f", k, 100.0 * (double)pd.meta.h_stats[8 + k] / (double)(tot ? tot : 1));
-            fprintf(stderr, "  (avg cycles/frame %.0f)\n", (double)tot / (double)pd.nfr);
+            for (int k = 0; k < 11; k++) tot += pd.meta.h_stats[8 + k];
+            fprintf(stderr, "phase cycles/frame:");
+            for (int k = 0; k < 11; k++) fprintf(stderr, " %d:%.0f", k, (double)pd.meta.h_stats[8 + k] / (double)pd.nfr);
+            fprintf(stderr, "  (total %.0f; look-back retries/frame %.2f)\n", (double)tot / (double)pd.nfr,
+                    (double)pd.meta.h_stats[8 + 11] / (double)pd.nfr);
         }
 #endif
         ood += pd.meta.h_stats[6];
@@ -867,6 +911,57 @@ extern "C" int flacb_encode_pcm(flacb_ctx *c, const void *pcm, uint64_t n_sample
 
 /* ------------------------------------------------------------------------------------- */
 
+/* Last step of a decode: inter-channel decorrelation + interleave (decoder.py:431-451) into the
+ * caller's buffer.  FLACB_E_NOSPACE leaves the decoded frames pending in the context, with the
+ * size that is needed in *n_sample_frames and *frame_channels: flacb_decode_output finishes. */
+static int decode_emit(flacb_ctx *c, uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
+                       int *frame_channels, flacb_stats *stats)
+{
+    const u64 total = c->pend_dec.total, nsf = c->pend_dec.nsf;
+    const int fch = c->pend_dec.fch;
+    if (n_sample_frames) *n_sample_frames = nsf;
+    if (frame_channels) *frame_channels = fch;
+    if (total > cap_samples) return FLACB_E_NOSPACE;
+    if (total && !pcm_out) return FLACB_E_ASSERT;
+    int rc;
+    float d2h_ms = 0.f, k2_ms = 0.f;
+    int32_t *d_out = pcm_out;
+    if (!(flags & FLACB_OUTPUT_ON_DEVICE)) {
+        if ((rc = c->d_pcm.ensure((total + 16) * 4))) return rc;
+        d_out = (int32_t *)c->d_pcm.p;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_k0, c->stream));
+    if (total) {
+        interleave_kernel<<<(unsigned)c->pend_dec.n_cand, 256, 0, c->stream>>>((const Candidate *)c->d_cand.p, (const int32_t *)c->d_frames.p,
+                                                                               d_out, total, fch);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
+    if (!(flags & FLACB_OUTPUT_ON_DEVICE) && total) {
+        /* same stream: the copy starts when the kernel is done, and its events time the copy alone */
+        CUDA_TRY(cudaEventRecord(c->ev_d0, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(pcm_out, d_out, total * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_d1, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c->ev_d0, c->ev_d1));
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    CUDA_TRY(cudaEventElapsedTime(&k2_ms, c->ev_k0, c->ev_k1));
+    c->pend_dec.valid = false;
+    if (stats) {
+        stats->frames = c->pend_dec.n_frames;
+        stats->subframes = c->pend_dec.n_frames * (u64)(fch > 0 ? fch : 0);
+        stats->bytes_out = total * 4;
+        stats->first_bad_frame = c->pend_dec.status ? (int64_t)c->pend_dec.n_frames : -1;
+        stats->kernel_ms = c->pend_dec.k_ms + k2_ms;
+        stats->h2d_ms = c->pend_dec.h2d_ms;
+        stats->d2h_ms = d2h_ms;
+    }
+    return c->pend_dec.status;
+}
+
 static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
                               uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
                               int *frame_channels, flacb_stats *stats, int check_crc8)
@@ -878,11 +973,12 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
         stats->first_bad_frame = -1;
     }
     if (!c || (!frames && len)) return FLACB_E_ASSERT;
+    c->pend_dec.valid = false;
     if (len < 2) return FLACB_OK; /* decoder.py:104-108: EOFError ends the frame loop */
     if (len >= (1ull << 40)) return FLACB_E_UNSUPPORTED;
     CUDA_TRY(cudaSetDevice(c->device));
     int rc;
-    float h2d_ms = 0.f, d2h_ms = 0.f, k_ms = 0.f;
+    float h2d_ms = 0.f, k_ms = 0.f;
     const uint8_t *d_s = frames;
     if (!(flags & FLACB_INPUT_ON_DEVICE)) {
         if ((rc = c->d_stream.ensure(len))) return rc;
@@ -966,48 +1062,24 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     const int fch = h_res->frame_channels;
     rc = h_res->status;
     if (rc == STATUS_CRC8_MISMATCH || rc == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH; /* the chain reached a frame with a bad header CRC: caller retries unfiltered */
-    const u64 total = nsf * (u64)(fch > 0 ? fch : 1);
-    if (total > cap_samples) {
-        CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
-        return FLACB_E_NOSPACE;
-    }
-    int32_t *d_out = pcm_out;
-    if (!(flags & FLACB_OUTPUT_ON_DEVICE)) {
-        if ((rc = c->d_pcm.ensure((total + 16) * 4))) return rc;
-        d_out = (int32_t *)c->d_pcm.p;
-        rc = h_res->status;
-    }
-    if (total) {
-        interleave_kernel<<<(unsigned)n_cand, 256, 0, c->stream>>>(d_cand, d_tmp, d_out, total, fch);
-        g_launches++;
-        CUDA_TRY(cudaGetLastError());
-    }
     CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
-    if (!(flags & FLACB_OUTPUT_ON_DEVICE) && total) {
-        CUDA_TRY(cudaEventRecord(c->ev_c0, c->copy_stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        CUDA_TRY(cudaMemcpyAsync(pcm_out, d_out, total * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-        CUDA_TRY(cudaEventRecord(c->ev_c1, c->copy_stream));
-        CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
-        CUDA_TRY(cudaEventElapsedTime(&d2h_ms, c->ev_c0, c->ev_c1));
-    } else {
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&k_ms, c->ev_k0, c->ev_k1));
-    if (n_sample_frames) *n_sample_frames = nsf;
-    if (frame_channels) *frame_channels = fch;
+    if (!(flags & FLACB_INPUT_ON_DEVICE)) CUDA_TRY(cudaEventElapsedTime(&h2d_ms, c->ev_c0, c->ev_c1));
+    c->pend_dec.valid = true;
+    c->pend_dec.n_cand = n_cand;
+    c->pend_dec.total = nsf * (u64)(fch > 0 ? fch : 1);
+    c->pend_dec.nsf = nsf;
+    c->pend_dec.n_frames = h_res->n_frames;
+    c->pend_dec.fch = fch;
+    c->pend_dec.status = rc;
+    c->pend_dec.k_ms = k_ms;
+    c->pend_dec.h2d_ms = h2d_ms;
     if (stats) {
-        stats->frames = h_res->n_frames;
-        stats->subframes = h_res->n_frames * (u64)(fch > 0 ? fch : 0);
         stats->bytes_in = len;
-        stats->bytes_out = total * 4;
-        stats->first_bad_frame = rc ? (int64_t)h_res->n_frames : -1;
-        stats->kernel_ms = k_ms;
-        stats->h2d_ms = h2d_ms;
-        stats->d2h_ms = d2h_ms;
         stats->out_of_domain = n_cand - h_res->n_frames; /* sync candidates that were not frames */
     }
-    return rc;
+    return decode_emit(c, flags, pcm_out, cap_samples, n_sample_frames, frame_channels, stats);
 }
 
 extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
@@ -1024,4 +1096,16 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
         rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, pcm_out, cap_samples, n_sample_frames,
                                 frame_channels, stats, 0);
     return rc;
+}
+
+extern "C" int flacb_decode_output(flacb_ctx *c, uint32_t flags, int32_t *pcm_out, uint64_t cap_samples,
+                                   uint64_t *n_sample_frames, int *frame_channels, flacb_stats *stats)
+{
+    if (!c || !c->pend_dec.valid) return FLACB_E_ASSERT;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->first_bad_frame = -1;
+    }
+    return decode_emit(c, flags, pcm_out, cap_samples, n_sample_frames, frame_channels, stats);
 }

@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(1024) chain_kernel(Candidate *cand, uint32_t n
 {
     __shared__ u64 warp_tot[32];
     __shared__ u64 carry;
-    __shared__ uint32_t first_bad, first_break, last_ok1;
+    __shared__ uint32_t first_bad, first_break, first_change, last_ok1;
     __shared__ int changed;
     const uint32_t NONE = 0xFFFFFFFFu;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -842,17 +842,23 @@ __global__ void __launch_bounds__(1024) chain_kernel(Candidate *cand, uint32_t n
         if (!any) break;
     }
     /* first chain frame the reference fails in, first chain frame after which sync is lost */
-    if (tid == 0) first_bad = NONE, first_break = NONE, last_ok1 = 0;
+    if (tid == 0) first_bad = NONE, first_break = NONE, first_change = NONE, last_ok1 = 0;
     __syncthreads();
+    const int nch0 = cand[0].nch;
     for (uint32_t c = tid; c < n; c += T) {
         if (!reach[c]) continue;
         const Candidate cc = cand[c];
+        if (cc.status == FLACB_OK && cc.nch != nch0) atomicMin(&first_change, c);
         if (cc.status != FLACB_OK) atomicMin(&first_bad, c);
         else if (cc.next == NONE && cc.end + 1 < len) atomicMin(&first_break, c);
     }
     /* a chain link can also point at a candidate whose own parse failed: covered by first_bad */
     __syncthreads();
-    const uint32_t stop = first_bad; /* frames with index >= stop are not produced */
+    /* The output is one interleaved array: a chain frame with another channel count than frame 0
+     * (the reference yields rows of another width from there on, decoder.py:52-55) ends the
+     * decode with FLACB_E_UNSUPPORTED; the frames in front of it are produced. */
+    const bool change_stop = first_change < first_bad && (first_break == NONE || first_change <= first_break);
+    const uint32_t stop = change_stop ? first_change : first_bad; /* frames with index >= stop are not produced */
     /* exclusive scan of block sizes over chain frames before `stop` */
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -893,6 +899,9 @@ __global__ void __launch_bounds__(1024) chain_kernel(Candidate *cand, uint32_t n
             /* the stream does not start with a frame: decoder.py:137 sync assert, unless there
              * are fewer than two bytes at all */
             status = len >= 2 ? FLACB_E_ASSERT : FLACB_OK;
+        } else if (change_stop) {
+            status = FLACB_E_UNSUPPORTED;
+            res->bad_frame = first_change;
         } else if (first_bad != NONE && (first_break == NONE || first_bad <= first_break)) {
             const int s = cand[first_bad].status;
             status = s == FLACB_E_EOF ? FLACB_OK : s; /* truncated last frame: dropped silently */

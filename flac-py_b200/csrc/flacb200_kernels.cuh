@@ -231,7 +231,7 @@ __host__ __device__ __forceinline__ uint32_t swz2(uint32_t i)
 struct SerLayout {
     uint32_t xwords;    /* words of one plane: guard + threads * S */
     uint32_t pstride;   /* words between two planes: = 4 (mod 32), so that the same sample of two channels lies 4 banks apart */
-    uint32_t planes, kall, kall_stride, cumw, stg, stg_words, total;
+    uint32_t planes, kall, kall_stride, cumw, partf, stg, stg_words, total;
     int S;
 };
 
@@ -253,6 +253,7 @@ __host__ __device__ inline SerLayout make_ser_layout(int nmax, int channels, int
     l.kall_stride = align16(2u << rmax);
     l.kall = off; off += l.kall_stride * (uint32_t)channels;
     l.cumw = off; off += align16((uint32_t)threads * 8u);
+    l.partf = off; off += align16((uint32_t)channels * (uint32_t)((threads + 31) / 32) * 5u * 8u); /* fixed-predictor errors per warp */
     l.stg = off;
     const uint32_t per = subframe_bound_bytes(nmax, bps, rmax);
     const uint32_t want = (per * (uint32_t)channels + 64 + 3) / 4 + 16; /* the whole frame */
@@ -1416,8 +1417,10 @@ static __device__ __noinline__ void resolve_offset(Shared *shp, int tid)
                 const int first_prefix = has_prefix ? __ffs((int)has_prefix) - 1 : 32;
                 const unsigned need = first_prefix == 32 ? FULL : ((2u << first_prefix) - 1u);
                 if (invalid & need) { /* a predecessor has not published yet */
-                    if (++spins > (1u << 22)) { failed = true; break; }
-                    __nanosleep(64);
+                    /* predecessors are resident (ticket order) and will publish; the bound only catches a
+                     * dead predecessor, after minutes, not a time-sliced or profiled GPU */
+                    if (++spins > (1u << 30)) { failed = true; break; }
+                    __nanosleep(spins < 64 ? 64 : 256);
                     continue;
                 }
                 u64 v = (lane <= first_prefix) ? (s & LB_VALUE) : 0ull;

@@ -21,15 +21,17 @@ enum KernelKind {
     K_FIXED2 = 5     /* serialise_kernel<.., false>: fixed predictors only, one kernel           */
 };
 
-/* serialise_kernel variants: samples per thread S = 8 R and launch bounds */
-struct SerVariant { int R, max_threads, ctas; };
+/* serialise_kernel variants: samples per thread, launch bounds (threads, frames per SM), registers that leaves */
+constexpr int SER_VARIANTS = 5;
+struct SerVariant { int S, max_threads, ctas, regs; };
 inline SerVariant ser_variant(int v)
 {
     switch (v) {
-    case 0: return {2, 288, 3};
-    case 1: return {2, 1024, 1};
-    case 2: return {1, 576, 1};
-    default: return {4, 512, 1};
+    case 0: return {16, 288, 3, 72};
+    case 1: return {16, 1024, 1, 64};
+    case 2: return {8, 576, 1, 112};
+    case 3: return {32, 512, 1, 128};
+    default: return {12, 384, 3, 56}; /* 12 warps: the same number on each of the SM's four schedulers */
     }
 }
 

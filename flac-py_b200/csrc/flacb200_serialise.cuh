@@ -11,24 +11,32 @@
  * its time waiting at block barriers (4.6 warps stalled on a barrier per issued instruction,
  * about 65 barriers per stereo frame):
  *
- *   - a thread owns S = 8 R CONSECUTIVE samples of every channel (the first kernel: runs of 8,
+ *   - a thread owns S CONSECUTIVE samples of every channel (the first kernel: runs of 8,
  *     tile-strided).  One block scan per channel gives both the partition sums of every
  *     candidate order and, later, the bit position of every code: no per-tile scans, no
  *     per-tile barriers.
  *   - the residual stays in the thread's registers from its computation to the sums over
  *     (u >> k); it is written back in place of the samples only for the packing phase, where
- *     every thread reads its own words again.
+ *     every thread reads its own words again.  Candidate orders whose partition of a span has
+ *     the same parameter share the sum.
  *   - decisions that used to be "thread 0 decides, barrier, everybody reads" are taken by every
  *     warp redundantly from per-warp partial sums: one barrier per reduction instead of two.
  *   - the serial fields (subframe header, warm-up samples, LPC header and coefficients) are
  *     or-ed in by different threads at closed-form bit positions while the others pack codes.
  *   - the whole frame is staged in shared memory when it fits and leaves with one flush;
- *     CRC-16 runs word-wise (slice-by-4 tables in shared memory) over balanced slices and is
- *     weighted with x^(8 * bytes behind) from a direct table: one table look-up and one
- *     carry-less multiply per thread instead of two multiplies per 64-byte slice.
+ *     CRC-16 runs word-wise (slice-by-4 tables in shared memory) over balanced slices, weighted
+ *     with x^(8 * bytes behind) from a direct table (one table look-up and one carry-less
+ *     multiply per thread instead of two multiplies per 64-byte slice), while warp 0 looks back
+ *     for the frame's offset.
  *
- * About 13 barriers per stereo frame.  Channel planes are XOR-swizzled on 16-byte units so that
- * a quarter warp's 16-byte accesses at strides of 32 / 64 / 128 bytes hit every bank once.
+ * 14 barriers per stereo frame.  Channel planes are XOR-swizzled on 16-byte units so that a
+ * quarter warp's 16-byte accesses at strides of 32 / 64 / 128 bytes hit every bank once.
+ *
+ * Measured and NOT kept (profiles/README.md, round 2): persistent CTAs with a prefetched ticket,
+ * Rice parameters per warp by shuffles instead of per block behind a barrier, one scan barrier
+ * for all channels, the previous frame's copy-out deferred into the next frame's round (it does
+ * remove the look-back waits, 4-10 retries per frame -> 0.1, but the SM's other frames had been
+ * using those cycles anyway): each of them made the kernel 10-15 % slower or changed nothing.
  *
  * Limits (the host falls back to encode_frames_kernel outside them): every plane resident,
  * block <= 1024 * S samples, Rice partition orders <= 8, a staging window that holds at least
@@ -42,12 +50,62 @@ namespace flacb {
 
 #ifndef FLACB_HOST_ONLY
 
-#if defined(FLACB_CPU_SIM) && defined(FLACB_SIM_TRACE)
-#include <stdio.h>
-#define V2_TRACE(tid, msg) do { if ((tid) == 0) fprintf(stderr, "v2: %s\n", msg); } while (0)
-#else
-#define V2_TRACE(tid, msg) do { } while (0)
-#endif
+
+/* crc.py:17-22 crc8, polynomial 0x107 (common.py:12): table of the byte-wise form */
+static __constant__ uint8_t c_crc8_tab[256] = {
+    0x00,0x07,0x0E,0x09,0x1C,0x1B,0x12,0x15,0x38,0x3F,0x36,0x31,0x24,0x23,0x2A,0x2D,0x70,0x77,0x7E,0x79,0x6C,0x6B,0x62,0x65,0x48,0x4F,0x46,0x41,0x54,0x53,0x5A,0x5D,
+    0xE0,0xE7,0xEE,0xE9,0xFC,0xFB,0xF2,0xF5,0xD8,0xDF,0xD6,0xD1,0xC4,0xC3,0xCA,0xCD,0x90,0x97,0x9E,0x99,0x8C,0x8B,0x82,0x85,0xA8,0xAF,0xA6,0xA1,0xB4,0xB3,0xBA,0xBD,
+    0xC7,0xC0,0xC9,0xCE,0xDB,0xDC,0xD5,0xD2,0xFF,0xF8,0xF1,0xF6,0xE3,0xE4,0xED,0xEA,0xB7,0xB0,0xB9,0xBE,0xAB,0xAC,0xA5,0xA2,0x8F,0x88,0x81,0x86,0x93,0x94,0x9D,0x9A,
+    0x27,0x20,0x29,0x2E,0x3B,0x3C,0x35,0x32,0x1F,0x18,0x11,0x16,0x03,0x04,0x0D,0x0A,0x57,0x50,0x59,0x5E,0x4B,0x4C,0x45,0x42,0x6F,0x68,0x61,0x66,0x73,0x74,0x7D,0x7A,
+    0x89,0x8E,0x87,0x80,0x95,0x92,0x9B,0x9C,0xB1,0xB6,0xBF,0xB8,0xAD,0xAA,0xA3,0xA4,0xF9,0xFE,0xF7,0xF0,0xE5,0xE2,0xEB,0xEC,0xC1,0xC6,0xCF,0xC8,0xDD,0xDA,0xD3,0xD4,
+    0x69,0x6E,0x67,0x60,0x75,0x72,0x7B,0x7C,0x51,0x56,0x5F,0x58,0x4D,0x4A,0x43,0x44,0x19,0x1E,0x17,0x10,0x05,0x02,0x0B,0x0C,0x21,0x26,0x2F,0x28,0x3D,0x3A,0x33,0x34,
+    0x4E,0x49,0x40,0x47,0x52,0x55,0x5C,0x5B,0x76,0x71,0x78,0x7F,0x6A,0x6D,0x64,0x63,0x3E,0x39,0x30,0x37,0x22,0x25,0x2C,0x2B,0x06,0x01,0x08,0x0F,0x1A,0x1D,0x14,0x13,
+    0xAE,0xA9,0xA0,0xA7,0xB2,0xB5,0xBC,0xBB,0x96,0x91,0x98,0x9F,0x8A,0x8D,0x84,0x83,0xDE,0xD9,0xD0,0xD7,0xC2,0xC5,0xCC,0xCB,0xE6,0xE1,0xE8,0xEF,0xFA,0xFD,0xF4,0xF3};
+
+/* encoder.py:194-234 put_frame_header (+ coded_number.py:7-39, crc.py:17-22), table CRC-8 */
+static __device__ __noinline__ int build_frame_header_v2(uint32_t flags, int channels, int bs, u64 number, uint8_t *h)
+{
+    int code = 0, extra = 0;
+    switch (bs) { /* common.py:85-105 */
+    case 192: code = 1; break;
+    case 576: code = 2; break;
+    case 1152: code = 3; break;
+    case 2304: code = 4; break;
+    case 4608: code = 5; break;
+    case 256: code = 8; break;
+    case 512: code = 9; break;
+    case 1024: code = 10; break;
+    case 2048: code = 11; break;
+    case 4096: code = 12; break;
+    case 8192: code = 13; break;
+    case 16384: code = 14; break;
+    case 32768: code = 15; break;
+    default:
+        if (bs <= 255) code = 6, extra = 8; /* encoder.py:245-255 */
+        else code = 7, extra = 16;
+    }
+    int len = 0;
+    h[len++] = 0xFF; /* sync 0x7FFC (15 bits) + blocking strategy 0 */
+    h[len++] = 0xF8;
+    h[len++] = (uint8_t)(code << 4); /* sample rate 0000: from STREAMINFO (encoder.py:94) */
+    const uint32_t chn = (flags & FLACB_SPEC_CHANNELS) ? (uint32_t)(channels - 1) : 1u; /* encoder.py:95 */
+    h[len++] = (uint8_t)(chn << 4); /* sample size 000 + reserved 0 (encoder.py:96) */
+    const int nb = 64 - __clzll(number | 1ull) - ((number == 0) ? 1 : 0);
+    if (nb <= 7) h[len++] = (uint8_t)number;
+    else {
+        const int size = nb <= 11 ? 2 : nb <= 16 ? 3 : nb <= 21 ? 4 : nb <= 26 ? 5 : 6;
+        for (int i = 0; i < size; i++) {
+            const uint8_t six = (uint8_t)((number >> (6 * (size - 1 - i))) & 0x3F);
+            h[len++] = i == 0 ? (uint8_t)((((1u << size) - 1u) << (8 - size)) | six) : (uint8_t)(0x80 | six);
+        }
+    }
+    if (extra == 8) h[len++] = (uint8_t)(bs - 1);
+    else if (extra == 16) h[len++] = (uint8_t)((bs - 1) >> 8), h[len++] = (uint8_t)(bs - 1);
+    uint32_t crc = 0;
+    for (int i = 0; i < len; i++) crc = c_crc8_tab[crc ^ h[i]];
+    h[len++] = (uint8_t)crc;
+    return len;
+}
 
 struct SerShared {
     Decision dec[MAX_CH];
@@ -195,13 +253,12 @@ static __device__ __noinline__ void load_planes_v2(const uint8_t *base, int32_t 
 /* ------------------------------------------------------------------------------------- */
 /* frame offset by decoupled look-back (same protocol as resolve_offset of the first kernel) */
 
-static __device__ __noinline__ void resolve_offset_v2(SerShared *shp, int tid)
+static __device__ __noinline__ void look_back_warp(SerShared *shp, int lane)
 {
     SerShared &sh = *shp;
-    const int lane = tid & 31, warp = tid >> 5;
     const uint32_t f = sh.frame;
     u64 *lb_state = sh.o_lb_state;
-    if (warp == 0) {
+    {
         const u64 mine = (u64)sh.frame_bytes;
         u64 excl = 0;
         bool failed = false;
@@ -243,6 +300,11 @@ static __device__ __noinline__ void resolve_offset_v2(SerShared *shp, int tid)
             sh.have_off = 1;
         }
     }
+}
+
+static __device__ __noinline__ void resolve_offset_v2(SerShared *shp, int tid)
+{
+    if (tid < 32) look_back_warp(shp, tid);
     __syncthreads();
 }
 
@@ -256,12 +318,11 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
                                              uint32_t nbytes, uint32_t wend, int last)
 {
     SerShared &sh = *shp;
-    const int have_off = sh.have_off; /* read in front of the barrier: resolve_offset_v2 sets it behind it */
+    const int have_off = sh.have_off; /* read in front of the barrier: look_back_warp sets it behind it */
     __syncthreads();
-    if (!have_off) resolve_offset_v2(shp, tid); /* block-uniform */
     const uint32_t byte0 = sh.wbase * 4u;          /* frame-relative */
-    V2_TRACE(tid, "resolved");
-    if (sh.writable && nbytes) {
+    auto copy_out = [&]() {
+        if (!(sh.writable && nbytes)) return;
         /* staging words hold the stream MSB first; memory wants those bytes in order.  Aligned
          * 32-bit stores for the body, single bytes in front of / behind it. */
         uint8_t *dst = sh.o_out + sh.frame_off + byte0;
@@ -284,37 +345,44 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
                 dstw[q] = __byte_perm(big, 0, 0x0123);
             }
         }
-    }
-    V2_TRACE(0, tid == 100 ? "copied 100" : tid == 287 ? "copied 287" : "copied");
-    /* CRC-16, slice-by-4: c' = T3[v >> 24] ^ T2[v >> 16 & 255] ^ T1[v >> 8 & 255] ^ T0[v & 255], v = (c << 16) ^ word */
-    const uint32_t nwords = nbytes >> 2, rem = nbytes & 3u;
-    const uint32_t sw = (nwords + (uint32_t)B - 1) / (uint32_t)B;
-    {
-        const uint32_t w0 = (uint32_t)tid * sw;
-        uint32_t w1 = w0 + sw < nwords ? w0 + sw : nwords;
-        const bool tail_owner = rem && (sw ? ((uint32_t)tid == (nwords - 1) / sw && nwords > 0) : false);
-        const bool only_tail = rem && nwords == 0 && tid == 0;
-        if (w0 < nwords || only_tail) {
-            uint32_t c = 0;
-            if (w0 >= nwords) w1 = w0;
-            for (uint32_t q = w0; q < w1; q++) {
-                const uint32_t v = stg[q] ^ (c << 16);
-                c = (uint32_t)sh.crc4[3][v >> 24] ^ (uint32_t)sh.crc4[2][(v >> 16) & 255u] ^ (uint32_t)sh.crc4[1][(v >> 8) & 255u] ^
-                    (uint32_t)sh.crc4[0][v & 255u];
-            }
-            uint32_t hi_byte = w1 * 4u;
-            if (tail_owner || only_tail) {
-                for (uint32_t idx = nwords * 4u; idx < nbytes; idx++) {
-                    const uint32_t byte = (stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
-                    c = ((c << 8) ^ (uint32_t)sh.crc4[0][(c >> 8) ^ byte]) & 0xFFFFu;
-                }
-                hi_byte = nbytes;
-            }
-            const uint32_t behind = sh.payload_bytes - (byte0 + hi_byte);
-            if (c) atomicXor(&sh.crc, gf16_mul(c, (uint32_t)crc_w[behind]));
+    };
+    /* CRC-16, slice-by-4: c' = T3[v >> 24] ^ T2[v >> 16 & 255] ^ T1[v >> 8 & 255] ^ T0[v & 255], v = (c << 16) ^ word;
+     * worker t of nt */
+    auto crc_slices = [&](int t, int nt) {
+        const uint32_t nwords = nbytes >> 2, rem = nbytes & 3u;
+        const uint32_t sw = (nwords + (uint32_t)nt - 1) / (uint32_t)nt;
+        const uint32_t w0 = (uint32_t)t * sw;
+        const bool tail_owner = rem && (nwords == 0 ? t == 0 : (uint32_t)t == (nwords - 1) / sw);
+        if (w0 >= nwords && !tail_owner) return;
+        const uint32_t w1 = w0 >= nwords ? w0 : (w0 + sw < nwords ? w0 + sw : nwords);
+        uint32_t c = 0;
+        for (uint32_t q = w0; q < w1; q++) {
+            const uint32_t v = stg[q] ^ (c << 16);
+            c = (uint32_t)sh.crc4[3][v >> 24] ^ (uint32_t)sh.crc4[2][(v >> 16) & 255u] ^ (uint32_t)sh.crc4[1][(v >> 8) & 255u] ^
+                (uint32_t)sh.crc4[0][v & 255u];
         }
+        uint32_t hi_byte = w1 * 4u;
+        if (tail_owner) {
+            for (uint32_t idx = nwords * 4u; idx < nbytes; idx++) {
+                const uint32_t byte = (stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
+                c = ((c << 8) ^ (uint32_t)sh.crc4[0][(c >> 8) ^ byte]) & 0xFFFFu;
+            }
+            hi_byte = nbytes;
+        }
+        const uint32_t behind = sh.payload_bytes - (byte0 + hi_byte);
+        if (c) atomicXor(&sh.crc, gf16_mul(c, (uint32_t)crc_w[behind]));
+    };
+    if (last && !have_off && B > 32) {
+        /* warp 0 looks back for the frame's offset while the others work on the CRC */
+        if (tid < 32) look_back_warp(shp, tid);
+        else crc_slices(tid - 32, B - 32);
+        __syncthreads();
+        copy_out();
+        return;
     }
-    V2_TRACE(0, tid == 100 ? "crc done 100" : tid == 287 ? "crc done 287" : "crc done");
+    if (!have_off) resolve_offset_v2(shp, tid); /* block-uniform */
+    copy_out();
+    crc_slices(tid, B);
     if (last) {
         __syncthreads();
         return;
@@ -394,10 +462,10 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
             u64 acc[5] = {0, 0, 0, 0, 0};
             if (i0 >= 4 && i0 + S <= n) {
 #pragma unroll
-                for (int e0 = 0; e0 < S; e0 += 8) { /* eight terms below 2^28 fit 32 bits */
+                for (int e0 = 0; e0 < S; e0 += 4) { /* four terms below 2^28 fit 32 bits */
                     uint32_t t[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-                    for (int e = e0; e < e0 + 8; e++) {
+                    for (int e = e0; e < e0 + 4; e++) {
                         t[0] += (uint32_t)abs(a[e + 4]), t[1] += (uint32_t)abs(r1[e + 3]), t[2] += (uint32_t)abs(r2[e + 2]);
                         t[3] += (uint32_t)abs(r3[e + 1]), t[4] += (uint32_t)abs(r4[e]);
                     }
@@ -478,20 +546,20 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
             if (((u64)qa << (p.bps - 1)) <= (1ull << 31) - 1) {
                 /* every partial sum fits 32 bits */
 #pragma unroll
-                for (int e0 = 0; e0 < S; e0 += 8) {
-                    int acc[8];
+                for (int e0 = 0; e0 < S; e0 += 4) {
+                    int acc[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) acc[e] = 0;
+                    for (int e = 0; e < 4; e++) acc[e] = 0;
 #pragma unroll
                     for (int j = 0; j < LMAX; j++) {
                         if (j < ncoef) {
                             const int cj = d.q[j];
 #pragma unroll
-                            for (int e = 0; e < 8; e++) acc[e] += h[LMAX + e0 + e - 1 - j] * cj;
+                            for (int e = 0; e < 4; e++) acc[e] += h[LMAX + e0 + e - 1 - j] * cj;
                         }
                     }
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
+                    for (int e = 0; e < 4; e++) {
                         const i64 r = (i64)h[LMAX + e0 + e] - (i64)(acc[e] >> shift);
                         const u64 z = ((u64)r << 1) ^ (u64)(r >> 63);
                         if ((z >> 32) != 0 && i0 + e0 + e >= warm && i0 + e0 + e < n) range_bad = true;
@@ -537,9 +605,11 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
 
     /* candidate partition orders (encoder.py:664-667): both tests are monotone in the order */
     int o_first = p.rmin, o_last = -1;
-    for (int o = p.rmin; o <= p.rmax; o++) {
-        if ((n & ((1 << o) - 1)) == 0 && (n >> o) > warm) o_last = o;
-        else break;
+    {
+        int o = __ffs(n) - 1;
+        if (o > p.rmax) o = p.rmax;
+        while (o >= p.rmin && (n >> o) <= warm) o--;
+        o_last = o >= p.rmin ? o : -1;
     }
     const bool no_cand = o_last < 0; /* encoder.py:669 assert; laid out with order 0 so that the stream stays well formed */
     if (no_cand) o_first = 0, o_last = 0;
@@ -562,7 +632,6 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
         b.cumw[b.tid] = inc - ts;
         if (b.lane == 31) sh.wtot[b.warp] = inc;
     }
-    V2_TRACE(b.tid, "before #1");
     __syncthreads(); /* #1: every thread has its inputs in registers, span sums are visible */
     st2<S>(x, (uint32_t)(V2_GUARD + i0), u); /* residual in place of the samples */
     if (!aligned) __syncthreads();           /* partial spans are read from the plane */
@@ -592,7 +661,6 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
         atomicAdd(&sh.sizeB[par][ci], len * (uint32_t)(1 + k));
         if (k > 14) atomicOr(&sh.any5[par][ci], 1u);
     }
-    V2_TRACE(b.tid, "before #2");
     __syncthreads(); /* #2 */
 
     /* sum over the samples of u >> k for every candidate order (rice_size, encoder.py:756-760).
@@ -602,16 +670,20 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
         const uint32_t magic_f = sh.magic_f[par];
         if (aligned) {
             const uint32_t pf = i0 < n ? fast_div((uint32_t)i0, psz_f, magic_f) : 0u;
+            uint32_t kprev = 0xFFFFFFFFu, t32 = 0;
 #pragma unroll
             for (int j = 0; j < V2_MAXC; j++) {
                 if (j < ncand) { /* block-uniform */
                     const int o = o_first + j;
                     const uint32_t k0 = kall[(1u << o) + (pf >> (o_last - o))];
-                    uint32_t t32 = 0;
+                    if (k0 != kprev) {
+                        t32 = 0;
 #pragma unroll
-                    for (int e = 0; e < S; e++) t32 += u[e] >> k0;
-                    t32 = __reduce_add_sync(FULL, t32);
-                    if (b.lane == j) mine = t32;
+                        for (int e = 0; e < S; e++) t32 += u[e] >> k0;
+                        kprev = k0;
+                    }
+                    const uint32_t tot = __reduce_add_sync(FULL, t32);
+                    if (b.lane == j) mine = tot;
                 }
             }
         } else {
@@ -630,7 +702,6 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
         }
         if (b.lane < 12) sh.part[par][b.warp][b.lane] = mine;
     }
-    V2_TRACE(b.tid, "before #3");
     __syncthreads(); /* #3 */
     /* every warp: lane j adds up candidate j; first minimum of the reference's size estimate
      * (with its per-partition "+4", encoder.py:685-695) */
@@ -810,10 +881,9 @@ __device__ __forceinline__ void pack_channel(SerCtx &b, int c, const uint16_t *c
 
 /* ------------------------------------------------------------------------------------- */
 
-template <int LMAX, bool CHOSEN, int R, int TB, int MINB>
+template <int LMAX, bool CHOSEN, int S, int TB, int MINB>
 __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
 {
-    constexpr int S = 8 * R;
     FLACB_DYN_SMEM(smem);
     __shared__ SerShared sh;
     SerCtx b(p, sh);
@@ -830,7 +900,6 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
     b.cumw = (u64 *)(smem + lay.cumw);
     b.stg = (uint32_t *)(smem + lay.stg);
     b.stg_words = lay.stg_words;
-    V2_TRACE(b.tid, "top");
 
     if (b.tid == 0) {
         /* frames are taken in launch order so that every predecessor of a frame is already
@@ -843,16 +912,13 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
     if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0, sh.range_flag[b.tid] = 0;
     for (int i = b.tid; i < 512; i += b.B) ((uint32_t *)&sh.crc4[0][0])[i] = ((const uint32_t *)p.crc4)[i];
     for (uint32_t idx = (uint32_t)b.tid; idx < b.stg_words + 4u; idx += (uint32_t)b.B) b.stg[idx] = 0;
-    V2_TRACE(b.tid, "zeroed");
     __syncthreads();
-    V2_TRACE(b.tid, "entered");
     const uint32_t f = sh.frame;
     const int n = b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
 
     /* ---- frame/channel split ---- */
     load_planes_v2(p.pcm + (u64)f * (u64)p.block_size * (u64)p.channels * (u64)p.cbytes, b.planes, b.pstride, lay.xwords, n,
                    p.channels, p.cbytes, b.tid, b.B);
-    V2_TRACE(b.tid, "planes");
     if constexpr (CHOSEN) {
         /* LPC configurations: the choice of every subframe was made by choose_kernel */
         for (uint32_t i = (uint32_t)b.tid; i < (uint32_t)p.channels * (sizeof(Decision) / 4); i += (uint32_t)b.B) {
@@ -865,7 +931,6 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
         if (b.tid < p.channels) sh.chan_status[b.tid] = p.dec[(u64)f * (u64)p.channels + (u64)b.tid].status;
     }
 
-    V2_TRACE(b.tid, "loaded");
     /* ---- phase 1: sizes ---- */
     for (int c = 0; c < p.channels; c++) size_channel<LMAX, CHOSEN, S>(b, c);
 
@@ -873,7 +938,7 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
     if (b.tid == 0) {
         for (int c = p.channels - 1; c >= 0; c--) /* the frame's status: first failing channel */
             if (sh.chan_status[c]) sh.status = sh.chan_status[c];
-        sh.hdr_len = build_frame_header(p, n, p.first_frame_number + f, sh.hdr);
+        sh.hdr_len = build_frame_header_v2(p.flags, p.channels, n, p.first_frame_number + f, sh.hdr);
         uint32_t bits = (uint32_t)sh.hdr_len * 8u;
         for (int c = 0; c < p.channels; c++) {
             sh.chan_bit0[c] = bits;
@@ -884,17 +949,19 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
         sh.frame_bytes = sh.payload_bytes + 2u; /* + CRC-16 */
         p.frame_bytes[f] = sh.frame_bytes;
         atomicExch(&p.lb_state[f], f == 0 ? (LB_PREFIX | (u64)sh.frame_bytes) : (LB_AGG | (u64)sh.frame_bytes));
-        for (int i = 0; i < sh.hdr_len; i++) or_bits2(b.stg, 0, 8u * (uint32_t)i, sh.hdr[i], 8);
+        for (int i = 0; i < sh.hdr_len; i += 4) {
+            const int m = sh.hdr_len - i < 4 ? sh.hdr_len - i : 4;
+            uint32_t v = 0;
+            for (int k = 0; k < m; k++) v = (v << 8) | sh.hdr[i + k];
+            or_bits2(b.stg, 0, 8u * (uint32_t)i, v, 8 * m);
+        }
     }
     __syncthreads();
 
-    V2_TRACE(b.tid, "sized");
     /* ---- phase 2: serialise ---- */
     for (int c = 0; c < p.channels; c++) pack_channel<S>(b, c, p.crc_w);
-    V2_TRACE(b.tid, "packed");
     /* encoder.py:159-165: pad to a byte, CRC-16 over the whole frame, append big endian */
     flush_v2(&sh, b.stg, b.stg_words, p.crc_w, b.tid, b.B, sh.payload_bytes - sh.wbase * 4u, (sh.payload_bytes + 3u) >> 2, 1);
-    V2_TRACE(b.tid, "flushed");
     if (b.tid == 0) {
         if (sh.writable) {
             uint8_t *dst = p.out + sh.frame_off + sh.payload_bytes;

@@ -68,12 +68,13 @@ cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour
 #endif
         return variant ? launch_one(encode_frames_kernel<LM, 288, 3, true, 0>, grid, threads, smem, stream, p)
                        : launch_one(encode_frames_kernel<LM, 576, 1, true, 0>, grid, threads, smem, stream, p);
-    case K_SERIALISE2: /* serialise_kernel<LMAX, chosen, R, launch bounds> */
+    case K_SERIALISE2: /* serialise_kernel<LMAX, chosen, samples per thread, launch bounds> */
         switch (variant) {
-        case 0: return launch_one(serialise_kernel<LM, true, 2, 288, 3>, grid, threads, smem, stream, p);
-        case 1: return launch_one(serialise_kernel<LM, true, 2, 1024, 1>, grid, threads, smem, stream, p);
-        case 2: return launch_one(serialise_kernel<LM, true, 1, 576, 1>, grid, threads, smem, stream, p);
-        case 3: return launch_one(serialise_kernel<LM, true, 4, 512, 1>, grid, threads, smem, stream, p);
+        case 0: return launch_one(serialise_kernel<LM, true, 16, 288, 3>, grid, threads, smem, stream, p);
+        case 1: return launch_one(serialise_kernel<LM, true, 16, 1024, 1>, grid, threads, smem, stream, p);
+        case 2: return launch_one(serialise_kernel<LM, true, 8, 576, 1>, grid, threads, smem, stream, p);
+        case 3: return launch_one(serialise_kernel<LM, true, 32, 512, 1>, grid, threads, smem, stream, p);
+        case 4: return launch_one(serialise_kernel<LM, true, 12, 384, 3>, grid, threads, smem, stream, p);
         default: return cudaErrorInvalidValue;
         }
     default: return cudaErrorInvalidValue;
@@ -81,10 +82,11 @@ cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour
 #else
     if (kind == K_FIXED2) {
         switch (variant) {
-        case 0: return launch_one(serialise_kernel<4, false, 2, 288, 3>, grid, threads, smem, stream, p);
-        case 1: return launch_one(serialise_kernel<4, false, 2, 1024, 1>, grid, threads, smem, stream, p);
-        case 2: return launch_one(serialise_kernel<4, false, 1, 576, 1>, grid, threads, smem, stream, p);
-        case 3: return launch_one(serialise_kernel<4, false, 4, 512, 1>, grid, threads, smem, stream, p);
+        case 0: return launch_one(serialise_kernel<4, false, 16, 288, 3>, grid, threads, smem, stream, p);
+        case 1: return launch_one(serialise_kernel<4, false, 16, 1024, 1>, grid, threads, smem, stream, p);
+        case 2: return launch_one(serialise_kernel<4, false, 8, 576, 1>, grid, threads, smem, stream, p);
+        case 3: return launch_one(serialise_kernel<4, false, 32, 512, 1>, grid, threads, smem, stream, p);
+        case 4: return launch_one(serialise_kernel<4, false, 12, 384, 3>, grid, threads, smem, stream, p);
         default: return cudaErrorInvalidValue;
         }
     }
@@ -119,9 +121,9 @@ size_t FLACB_CAT(static_smem2_, FLACB_TU_NAME)()
 {
     cudaFuncAttributes fa;
 #if FLACB_TU_LMAX
-    if (cudaFuncGetAttributes(&fa, serialise_kernel<FLACB_TU_LMAX, true, 2, 288, 3>) != cudaSuccess) return 12288;
+    if (cudaFuncGetAttributes(&fa, serialise_kernel<FLACB_TU_LMAX, true, 16, 288, 3>) != cudaSuccess) return 12288;
 #else
-    if (cudaFuncGetAttributes(&fa, serialise_kernel<4, false, 2, 288, 3>) != cudaSuccess) return 12288;
+    if (cudaFuncGetAttributes(&fa, serialise_kernel<4, false, 16, 288, 3>) != cudaSuccess) return 12288;
 #endif
     return fa.sharedSizeBytes;
 }

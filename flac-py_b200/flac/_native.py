@@ -72,7 +72,7 @@ EXPORTS = [
     "flacb_version", "flacb_device_count", "flacb_strerror", "flacb_last_cuda_error",
     "flacb_create", "flacb_destroy", "flacb_host_alloc", "flacb_host_free", "flacb_device_alloc",
     "flacb_device_free", "flacb_memcpy_h2d", "flacb_memcpy_d2h", "flacb_encode_bound",
-    "flacb_encode_pcm", "flacb_stream_prologue", "flacb_decode_frames", "flacb_timer_begin",
+    "flacb_encode_pcm", "flacb_stream_prologue", "flacb_decode_frames", "flacb_decode_output", "flacb_timer_begin",
     "flacb_timer_end", "flacb_sync", "flacb_kernel_launches",
 ]
 
@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
         L.flacb_decode_frames.argtypes = [vp, vp, u64, i32, u32, vp, u64, C.POINTER(u64),
                                           C.POINTER(i32), C.POINTER(Stats)]
         L.flacb_timer_begin.restype = i32
+        L.flacb_decode_output.restype = i32
+        L.flacb_decode_output.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(i32), C.POINTER(Stats)]
         L.flacb_timer_begin.argtypes = [vp]
         L.flacb_timer_end.restype = i32
         L.flacb_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
@@ -246,6 +248,15 @@ class Context:
         rc = lib().flacb_decode_frames(self._h, C.c_void_p(frames_ptr), nbytes, streaminfo_bits,
                                        flags, C.c_void_p(out_ptr), cap_samples, C.byref(n),
                                        C.byref(fch), C.byref(st))
+        return rc, n.value, fch.value, st
+
+    def decode_output(self, flags: int, out_ptr: int, cap_samples: int):
+        """After decode_raw returned E_NOSPACE: write the frames it decoded (they are still in the
+        context) to a buffer of the size it reported."""
+        st = Stats()
+        n = C.c_uint64(0)
+        fch = C.c_int(0)
+        rc = lib().flacb_decode_output(self._h, flags, C.c_void_p(out_ptr), cap_samples, C.byref(n), C.byref(fch), C.byref(st))
         return rc, n.value, fch.value, st
 
 

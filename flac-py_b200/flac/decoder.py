@@ -42,20 +42,23 @@ def decode_frames_status(frames, sample_size: int, *, devices: Optional[Sequence
     front of the first one the reference decoder fails in, and that failure's status."""
     raw = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else frames
     ctx = N.default_context(devices[0] if devices else None)
-    # room for the decoded samples: STREAMINFO's count when the caller knows it (times the most
-    # channels a frame can carry), else a generous guess that is grown on demand
-    cap = (cap_sample_frames + 65536) * 8 if cap_sample_frames else max(raw.size * 16, 1 << 16)
-    while True:
+    # Room for the decoded samples.  STREAMINFO's 36-bit sample count is only a hint (the reference never
+    # allocates from it, and a wrong or hostile value must not turn into a terabyte of np.empty): it is
+    # clamped to what a stream of this many bytes plausibly holds; when the guess is too small the library
+    # says how much the stream decodes to and hands the frames it has already decoded over
+    # (flacb_decode_output), so nothing is decoded twice and nothing is sized from untrusted data.
+    guess = max(raw.size * 16, 1 << 16)
+    cap = min((cap_sample_frames + 65536) * 8, guess) if cap_sample_frames else guess
+    out = np.empty(cap, dtype=np.int32)
+    rc, n, fch, _ = ctx.decode_raw(raw.ctypes.data if raw.size else 0, raw.size, sample_size, 0, out.ctypes.data, cap)
+    if rc == N.E_NOSPACE:
+        cap = n * max(fch, 1)
         out = np.empty(cap, dtype=np.int32)
-        rc, n, fch, _ = ctx.decode_raw(raw.ctypes.data if raw.size else 0, raw.size, sample_size, 0,
-                                       out.ctypes.data, cap)
-        if rc == N.E_NOSPACE:
-            cap *= 4
-            continue
-        if rc in (N.E_CUDA, N.E_UNSUPPORTED, N.E_INTERNAL):
-            N.raise_for_status(rc, "decode")
-        fch = max(fch, 1)
-        return out[:n * fch].reshape(-1, fch), fch, rc
+        rc, n, fch, _ = ctx.decode_output(0, out.ctypes.data, cap)
+    if rc in (N.E_CUDA, N.E_UNSUPPORTED, N.E_INTERNAL, N.E_NOSPACE):
+        N.raise_for_status(rc, "decode")
+    fch = max(fch, 1)
+    return out[:n * fch].reshape(-1, fch), fch, rc
 
 
 def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,

@@ -164,6 +164,17 @@ int flacb_decode_frames(flacb_ctx *ctx, const uint8_t *frames, uint64_t len, int
                         uint32_t flags, int32_t *pcm_out, uint64_t cap_samples,
                         uint64_t *n_sample_frames, int *frame_channels, flacb_stats *stats);
 
+/*
+ * When flacb_decode_frames returns FLACB_E_NOSPACE, *n_sample_frames and *frame_channels hold what
+ * the stream decodes to and the decoded frames stay in the context: this call writes them to a
+ * buffer of at least n_sample_frames * frame_channels samples without decoding again.  (The
+ * reference never sizes anything in advance -- decoder.py:46-55 yields sample by sample -- and
+ * STREAMINFO's sample count is not to be trusted for an allocation.)  Valid until the next
+ * decode call on the context.
+ */
+int flacb_decode_output(flacb_ctx *ctx, uint32_t flags, int32_t *pcm_out, uint64_t cap_samples,
+                        uint64_t *n_sample_frames, int *frame_channels, flacb_stats *stats);
+
 /* CUDA-event timer on the context's stream, for the benchmark (kernel-only throughput). */
 int flacb_timer_begin(flacb_ctx *ctx);
 int flacb_timer_end(flacb_ctx *ctx, float *ms);

@@ -155,15 +155,14 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         }
     }
     /* plane_mode bit 11: the second-generation serialiser (flacb200_serialise.cuh); bits 12-13:
-     * samples per thread (0: 16, 1: 8, 2: 32); bit 14: a small staging window (mid-frame flushes) */
+     * samples per thread (0: 16, 1: 8, 2: 32, 3: 12); bit 14: a small staging window (mid-frame flushes) */
     const bool ser2 = (plane_mode & 0x800u) != 0;
     uint16_t crc4[4][256];
     std::vector<uint16_t> crc_w;
     if (ser2) {
         if (rice_max > V2_MAX_RICE || (flags & FLACB_SLOT_COMPACT)) return FLACB_E_UNSUPPORTED;
         const int rsel = (int)((plane_mode >> 12) & 3u);
-        const int R = rsel == 1 ? 1 : rsel == 2 ? 4 : 2;
-        const int S = 8 * R;
+        const int S = rsel == 1 ? 8 : rsel == 2 ? 32 : rsel == 3 ? 12 : 16;
         int Bt = ((block_size + S - 1) / S + 31) / 32 * 32;
         if (threads_override) Bt = threads_override;
         if (Bt > 1024 || Bt * S < block_size) return FLACB_E_UNSUPPORTED;
@@ -186,9 +185,10 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
             const size_t dyn2 = p.slay.total;
 #define SER_RUN(LM, CH)                                                                                         \
     do {                                                                                                        \
-        if (R == 1) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 1, 1024, 1>(p); });       \
-        else if (R == 2) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 2, 1024, 1>(p); });  \
-        else sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 4, 1024, 1>(p); });              \
+        if (S == 8) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 8, 1024, 1>(p); });        \
+        else if (S == 16) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 16, 1024, 1>(p); });  \
+        else if (S == 12) sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 12, 1024, 1>(p); });  \
+        else sim::run_block(fu, g, Bt, dyn2, [&]() { serialise_kernel<LM, CH, 32, 1024, 1>(p); });               \
     } while (0)
             if (!staged) SER_RUN(4, false);
             else if (max_lpc_order <= 12) SER_RUN(12, true);

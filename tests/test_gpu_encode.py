@@ -42,11 +42,11 @@ def test_golden_stream_bytes(name, mode):
     assert lens == case["chunk_lengths"]
 
 
-@pytest.mark.parametrize("ser", ["1", "2,0", "2,1", "2,2", "2,3", "2,0,1"])
+@pytest.mark.parametrize("ser", ["1", "2,0", "2,1", "2,2", "2,3", "2,4", "2,0,1"])
 @pytest.mark.parametrize("name", ["c1_sine", "c2_white", "c2_clip", "c3_white", "c4_mixed", "bs255", "bs1000", "q15_white24", "many_frames"])
 def test_golden_stream_bytes_every_serialiser(name, ser, monkeypatch):
     """FLACB200_SERIALISE=1: the first-generation serialising kernel (encode_frames_kernel); 2,<v>[,<frames per
-    SM>]: serialise_kernel with 16 / 16 / 8 / 32 samples per thread (the default picks the variant with the most
+    SM>]: serialise_kernel with 16 / 16 / 8 / 32 / 12 samples per thread (the default picks the variant with the most
     resident threads; a variant that cannot hold the block falls back to the first-generation kernel)"""
     monkeypatch.setenv("FLACB200_SERIALISE", ser)
     case = CASES[name]

@@ -188,17 +188,18 @@ def test_sim_decode_crafted_streams_like_the_reference(name):
 
 
 # ---- second-generation serialiser (flacb200_serialise.cuh): plane_mode bit 11; bits 12-13 pick the
-# samples per thread (16 / 8 / 32), bit 14 a staging window of one worst-case subframe (mid-frame flushes)
+# samples per thread (16 / 8 / 32 / 12), bit 14 a staging window of one worst-case subframe (mid-frame flushes)
 SER2 = 0x800
-SER2_MODES = {"s16": SER2, "s8": SER2 | 0x1000, "s32": SER2 | 0x2000, "s16_smallwin": SER2 | 0x4000}
+SER2_MODES = {"s16": SER2, "s8": SER2 | 0x1000, "s32": SER2 | 0x2000, "s12": SER2 | 0x3000, "s16_smallwin": SER2 | 0x4000}
 
 
 @pytest.mark.parametrize("mode", sorted(SER2_MODES))
 @pytest.mark.parametrize("name", FAST + ["many_frames"])
 def test_sim_serialise_kernel_matches_golden(name, mode):
     case = CASES[name]
-    if mode == "s8" and case["block_size"] > 8 * 1024:
-        pytest.skip("8 samples per thread: blocks up to 8192")
+    per_thread = {"s8": 8, "s12": 12}.get(mode, 16)
+    if case["block_size"] > per_thread * 1024:
+        pytest.skip(f"{per_thread} samples per thread: blocks up to {per_thread * 1024}")
     x = case_pcm(case)
     rc, data, offs, _, st = simlib.encode_frames(x, case["bits"], plane_mode=SER2_MODES[mode], **case_kwargs(case))
     assert rc == 0
@@ -214,7 +215,7 @@ def test_sim_serialise_kernel_other_shapes_against_the_oracle(ch, bits, L, q, bs
     import flacb200_synth as S
     x = S.pcm(bs * 3 + bs // 3 + 5, ch, bits, 48000, cls, 99 + ch + bits)
     ref = O.encode_frames(x, bits, bs, L, q, 0, 4)
-    for mode in (SER2, SER2 | 0x1000, SER2 | 0x4000):
+    for mode in (SER2, SER2 | 0x1000, SER2 | 0x3000, SER2 | 0x4000):
         rc, data, offs, info, st = simlib.encode_frames(x, bits, bs, L, q, 0, 4, plane_mode=mode, want_info=True)
         assert rc == 0 and data == ref.data and (offs == ref.frame_offsets).all(), hex(mode)
         rc1, data1, _, info1, _ = simlib.encode_frames(x, bits, bs, L, q, 0, 4, want_info=True)
