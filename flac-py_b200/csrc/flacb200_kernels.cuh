@@ -746,28 +746,107 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
     if (A >= Bq) A = top, Bq = top; /* no flat middle: one range */
     const int count = A + (top - Bq);
     const bool stored = (size_t)(count + (count >> 3) + 2) * 8 <= b.wx_bytes;
+    /* warp sum of LG double-double partials, transposing as it goes: after the first two exchanges
+     * (lanes 16 and 8 apart) a lane holds one lag's sum over four lanes, three ordinary butterfly
+     * steps finish it: 6 exchanges for 4 lags instead of 20 */
+    static_assert(LG == 4, "the transposed warp sum is written for four lags per pass");
+    auto warp_sum4 = [&](const double (&s)[LG], const double (&c)[LG], int lag0) {
+        const bool b4 = (b.lane & 16) != 0, b3 = (b.lane & 8) != 0;
+        auto xchg = [&](double &ks, double &kc, double ss, double sc, int off) {
+            const double s2 = __shfl_xor_sync(FULL, ss, off);
+            const double c2 = __shfl_xor_sync(FULL, sc, off);
+            dd_add(ks, kc, s2);
+            kc = __dadd_rn(kc, c2);
+        };
+        /* lanes 16 apart: the lower lane keeps lags 0, 1 and takes the partner's, the upper 2, 3 */
+        double k0s = b4 ? s[2] : s[0], k0c = b4 ? c[2] : c[0], k1s = b4 ? s[3] : s[1], k1c = b4 ? c[3] : c[1];
+        xchg(k0s, k0c, b4 ? s[0] : s[2], b4 ? c[0] : c[2], 16);
+        xchg(k1s, k1c, b4 ? s[1] : s[3], b4 ? c[1] : c[3], 16);
+        /* lanes 8 apart: the lower keeps the first of its two lags */
+        double ks = b3 ? k1s : k0s, kc = b3 ? k1c : k0c;
+        xchg(ks, kc, b3 ? k0s : k1s, b3 ? k0c : k1c, 8);
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) xchg(ks, kc, ks, kc, off);
+        const int lag = lag0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
+        if ((b.lane & 7) == 0 && lag <= L) part_d[b.warp * (FLACB_MAX_LPC + 1) + lag] = make_double2(ks, kc);
+    };
     if (stored) {
+        /* The last sample never enters a product (encoder.py:449, range(len - lag - 1): neither as the
+         * left nor as the right factor), and there are zeros behind it: with w[n - 1] stored as zero
+         * no product needs a range check.  (Adding a zero product changes neither part of a sum.) */
         for (int t = b.tid; t < count; t += b.B) {
             const int i = t < A ? t : Bq + (t - A);
-            wxs[t + (t >> 3)] = __dmul_rn((double)x[swz((uint32_t)(GUARD + i))], b.win[i]);
+            wxs[t + (t >> 3)] = i >= n - 1 ? 0.0 : __dmul_rn((double)x[swz((uint32_t)(GUARD + i))], b.win[i]);
         }
         __syncthreads();
-    }
-    for (int lag0 = 0; lag0 <= L; lag0 += LG) {
-        double s[LG], c[LG];
+        /* The tapered runs (everything autoc_flat() refuses) are the runs [0, RA) and [RB, nruns),
+         * T of them: thread t takes the runs number t, t + B, ... of that list, Q each -- and the
+         * R = T mod B runs that are left over (two of 290 at block 4608: one more full round would
+         * leave the block waiting for the one warp that holds them) are done by a warp each with
+         * a lane per LAG, eight products per lane instead of eight per lag. */
+        const int nruns = (n + E - 1) / E;
+        int RA = (b.flat_lo + E - 1) / E;
+        int lim = b.flat_hi - L - E;
+        if (lim > n - L - E - 1) lim = n - L - E - 1;
+        int RB = lim < 0 ? 0 : lim / E + 1;
+        if (RA < 0) RA = 0;
+        if (RA >= RB || RA >= nruns) RA = nruns, RB = nruns;
+        if (RB > nruns) RB = nruns;
+        const int T = RA + (nruns - RB);
+        int Q = T / b.B, R = T - Q * b.B;
+        if (R > 0 && (R + b.nwarps - 1) / b.nwarps >= L + 1) Q += 1, R = 0; /* too many for that: a round like the others */
+        const int Tmain = R ? Q * b.B : T;
+        auto run_pos = [&](int tau) { /* position of the run's first sample in wxs */
+            const int i0 = (tau < RA ? tau : RB + (tau - RA)) * E;
+            return i0 < A ? i0 : A + (i0 - Bq);
+        };
+        for (int lag0 = 0; lag0 <= L; lag0 += LG) {
+            double s[LG], c[LG];
 #pragma unroll
-        for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
-        for (int tile = 0; tile < b.ntiles; tile++) {
-            const int i0 = (tile * b.B + b.tid) * E;
-            if (i0 < n && !autoc_flat(b, i0, L)) {
+            for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
+            for (int tau = b.tid; tau < Tmain; tau += b.B) {
+                const int t0 = run_pos(tau); /* a thread's reads stay inside one range */
                 double wa[E], wb[E + LG - 1];
-                if (stored) {
-                    const int t0 = i0 < A ? i0 : A + (i0 - Bq); /* a thread's reads stay inside one range */
 #pragma unroll
-                    for (int e = 0; e < E; e++) wa[e] = wxs[(t0 + e) + ((t0 + e) >> 3)];
+                for (int e = 0; e < E; e++) wa[e] = wxs[(t0 + e) + ((t0 + e) >> 3)];
 #pragma unroll
-                    for (int j = 0; j < E + LG - 1; j++) wb[j] = wxs[(t0 + lag0 + j) + ((t0 + lag0 + j) >> 3)];
-                } else {
+                for (int j = 0; j < E + LG - 1; j++) wb[j] = wxs[(t0 + lag0 + j) + ((t0 + lag0 + j) >> 3)];
+#pragma unroll
+                for (int l = 0; l < LG; l++) {
+                    if (lag0 + l <= L) {
+#pragma unroll
+                        for (int e = 0; e < E; e++) dd_add(s[l], c[l], __dmul_rn(wa[e], wb[e + l]));
+                    }
+                }
+            }
+            warp_sum4(s, c, lag0);
+        }
+        if (R) {
+            __syncwarp(); /* this warp's partial sums are in part_d */
+            for (int j = b.warp; j < R; j += b.nwarps) {
+                const int t0 = run_pos(Q * b.B + j);
+                for (int lag = b.lane; lag <= L; lag += 32) {
+                    double ss = 0.0, cc = 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        dd_add(ss, cc, __dmul_rn(wxs[(t0 + e) + ((t0 + e) >> 3)], wxs[(t0 + e + lag) + ((t0 + e + lag) >> 3)]));
+                    double2 v = part_d[b.warp * (FLACB_MAX_LPC + 1) + lag];
+                    dd_add(v.x, v.y, ss);
+                    v.y = __dadd_rn(v.y, cc);
+                    part_d[b.warp * (FLACB_MAX_LPC + 1) + lag] = v;
+                }
+            }
+        }
+    } else {
+        /* the windowed ends do not fit the scratch area (very large blocks): windowed on the fly */
+        for (int lag0 = 0; lag0 <= L; lag0 += LG) {
+            double s[LG], c[LG];
+#pragma unroll
+            for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
+            for (int tile = 0; tile < b.ntiles; tile++) {
+                const int i0 = (tile * b.B + b.tid) * E;
+                if (i0 < n && !autoc_flat(b, i0, L)) {
+                    double wa[E], wb[E + LG - 1];
 #pragma unroll
                     for (int e = 0; e < E; e++)
                         wa[e] = __dmul_rn((double)x[swz((uint32_t)(GUARD + i0 + e))], b.win[i0 + e]);
@@ -776,43 +855,20 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                         const int idx = i0 + lag0 + j;
                         wb[j] = __dmul_rn((double)x[swz((uint32_t)(GUARD + idx))], b.win[idx]);
                     }
-                }
 #pragma unroll
-                for (int l = 0; l < LG; l++) {
-                    const int lag = lag0 + l;
-                    if (lag <= L) {
+                    for (int l = 0; l < LG; l++) {
+                        const int lag = lag0 + l;
+                        if (lag <= L) {
 #pragma unroll
-                        for (int e = 0; e < E; e++) {
-                            /* range(len - lag - 1): the last product is dropped (encoder.py:449) */
-                            if (i0 + e < n - lag - 1) dd_add(s[l], c[l], __dmul_rn(wa[e], wb[e + l]));
+                            for (int e = 0; e < E; e++) {
+                                /* range(len - lag - 1): the last product is dropped (encoder.py:449) */
+                                if (i0 + e < n - lag - 1) dd_add(s[l], c[l], __dmul_rn(wa[e], wb[e + l]));
+                            }
                         }
                     }
                 }
             }
-        }
-        /* warp sum of the LG double-double partials, transposing as it goes: after the first two
-         * exchanges (lanes 16 and 8 apart) a lane holds one lag's sum over four lanes, three
-         * ordinary butterfly steps finish it: 6 exchanges for 4 lags instead of 20 */
-        static_assert(LG == 4, "the transposed warp sum is written for four lags per pass");
-        {
-            const bool b4 = (b.lane & 16) != 0, b3 = (b.lane & 8) != 0;
-            auto xchg = [&](double &ks, double &kc, double ss, double sc, int off) {
-                const double s2 = __shfl_xor_sync(FULL, ss, off);
-                const double c2 = __shfl_xor_sync(FULL, sc, off);
-                dd_add(ks, kc, s2);
-                kc = __dadd_rn(kc, c2);
-            };
-            /* lanes 16 apart: the lower lane keeps lags 0, 1 and takes the partner's, the upper 2, 3 */
-            double k0s = b4 ? s[2] : s[0], k0c = b4 ? c[2] : c[0], k1s = b4 ? s[3] : s[1], k1c = b4 ? c[3] : c[1];
-            xchg(k0s, k0c, b4 ? s[0] : s[2], b4 ? c[0] : c[2], 16);
-            xchg(k1s, k1c, b4 ? s[1] : s[3], b4 ? c[1] : c[3], 16);
-            /* lanes 8 apart: the lower keeps the first of its two lags */
-            double ks = b3 ? k1s : k0s, kc = b3 ? k1c : k0c;
-            xchg(ks, kc, b3 ? k0s : k1s, b3 ? k0c : k1c, 8);
-#pragma unroll
-            for (int off = 4; off > 0; off >>= 1) xchg(ks, kc, ks, kc, off);
-            const int lag = lag0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
-            if ((b.lane & 7) == 0 && lag <= L) part_d[b.warp * (FLACB_MAX_LPC + 1) + lag] = make_double2(ks, kc);
+            warp_sum4(s, c, lag0);
         }
     }
     __syncthreads();

@@ -50,7 +50,7 @@ def main():
                 ks.append(st.kernel_ms)
         ms = float(np.median(ks))
         print(json.dumps({"workload": args.workload, "shape": t, "threads": st.threads_per_frame, "smem": st.smem_bytes,
-                          "kernel_ms": round(ms, 4), "Msamples/s": round(n * ch / ms / 1e3, 1),
+                          "kernel_ms": round(ms, 4), "stages_ms": [round(float(v), 4) for v in st.stage_ms], "Msamples/s": round(n * ch / ms / 1e3, 1),
                           "GB/s": round((raw.size + out_len) / ms / 1e6, 2), "bytes_out": out_len,
                           "ood": int(st.out_of_domain)}), flush=True)
     if args.decode:
