@@ -91,8 +91,8 @@ struct EncSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     cudaEvent_t ev_s[3] = {nullptr, nullptr, nullptr}; /* between the stages of the LPC pipeline */
-    bool staged = false;
-    DevBuf pcm, out, slots, frame_bytes, frame_off, status, lb, misc, info, pre, dec;
+    int staged = 0; /* 0: one kernel (its time under stage_ms[3]); 1: stages timed one by one; 2: stages overlapped, not timed */
+    DevBuf pcm, out, slots, frame_bytes, misc, info, pre, dec;
     HostBuf h_meta;
     bool d2h_pending = false;
 };
@@ -233,7 +233,7 @@ extern "C" void flacb_destroy(flacb_ctx *c)
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < FLACB_SLOTS; i++) {
         EncSlot &sl = c->slot[i];
-        DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.frame_off, &sl.status, &sl.lb, &sl.misc, &sl.info, &sl.pre, &sl.dec};
+        DevBuf *sb[] = {&sl.pcm, &sl.out, &sl.slots, &sl.frame_bytes, &sl.misc, &sl.info, &sl.pre, &sl.dec};
         for (DevBuf *b : sb) b->release();
         sl.h_meta.release();
         cudaEvent_t se[] = {sl.ev_k0, sl.ev_k1, sl.ev_c0, sl.ev_c1, sl.ev_d0, sl.ev_d1, sl.ev_s[0], sl.ev_s[1], sl.ev_s[2]};
@@ -476,12 +476,17 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     const SmemLayout lay_rec = make_layout(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, B, 0); /* record offsets */
 
     int rc; /* the window tables were uploaded by the caller before the first chunk */
+    /* One device block for everything a call clears and reads back, so that a call makes one memset and
+     * one copy to the host instead of two and three (per-call driver work is what separates the step time
+     * from the sum of the stages, more so with eight ranks on one host):
+     *   [frame_off u64 n+1][stats + ticket 512 B][status i32 n] | [look-back words u64 n]   <- cleared
+     *   `-------------------- copied to the host ------------'                                         */
+    const size_t o_foff = 0, o_misc = (n_frames + 1) * 8, o_status = o_misc + 512;
+    const size_t meta_bytes = (o_status + n_frames * 4 + 15) & ~(size_t)15, o_lb = meta_bytes;
     if ((rc = sl.frame_bytes.ensure(n_frames * 4))) return rc;
-    if ((rc = sl.frame_off.ensure((n_frames + 1) * 8))) return rc;
-    if ((rc = sl.status.ensure(n_frames * 4))) return rc;
-    if ((rc = sl.lb.ensure(n_frames * 8))) return rc;
-    if ((rc = sl.misc.ensure(512))) return rc;
-    if ((rc = sl.h_meta.ensure((n_frames + 1) * 8 + n_frames * 4 + 256 + 16))) return rc;
+    if ((rc = sl.misc.ensure(o_lb + n_frames * 8))) return rc;
+    if ((rc = sl.h_meta.ensure(meta_bytes + 16))) return rc;
+    uint8_t *dmeta = (uint8_t *)sl.misc.p;
 
     EncParams p;
     memset(&p, 0, sizeof(p));
@@ -508,11 +513,11 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     p.flat_tail_lo = own_tail ? c->flat_tail[0] : p.flat_full_lo;
     p.flat_tail_hi = own_tail ? c->flat_tail[1] : p.flat_full_hi;
     p.frame_bytes = (uint32_t *)sl.frame_bytes.p;
-    p.frame_off = (u64 *)sl.frame_off.p;
-    p.frame_status = (int32_t *)sl.status.p;
-    p.lb_state = (u64 *)sl.lb.p;
-    p.ticket = (uint32_t *)sl.misc.p;
-    p.stats = (u64 *)((uint8_t *)sl.misc.p + 64);
+    p.frame_off = (u64 *)(dmeta + o_foff);
+    p.frame_status = (int32_t *)(dmeta + o_status);
+    p.lb_state = (u64 *)(dmeta + o_lb);
+    p.ticket = (uint32_t *)(dmeta + o_misc);
+    p.stats = (u64 *)(dmeta + o_misc + 64);
     p.info = d_info;
     p.all_planes = shape.all_planes;
     p.lay = lay;
@@ -544,40 +549,59 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         const int v = atoi(e);
         if (v > flavour && v <= 2) flavour = v;
     }
+    /* stage events in between (FLACB_STAGE_TIMES) keep the stages apart; without them the stages behind the
+     * first are launched with programmatic stream serialisation (FLACB200_NO_PDL=1: plain launches) */
+    const bool stage_times = (a.flags & FLACB_STAGE_TIMES) != 0;
+    const bool pdl = !stage_times && plan.staged && !getenv("FLACB200_NO_PDL");
     auto launch = [&](int kind, int variant, int threads, size_t smem, const EncParams &kp) {
         g_launches++;
         const unsigned grid = (unsigned)n_frames;
-        if (kind == K_FIXED || kind == K_FIXED2) return launch_fixed(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
-        return plan.lmax12 ? launch_12(kind, variant, flavour, grid, threads, smem, sl.stream, kp)
-                           : launch_32(kind, variant, flavour, grid, threads, smem, sl.stream, kp);
+        const int fl = flavour | ((pdl && kind != K_ANALYSE) ? 0x100 : 0);
+        if (kind == K_FIXED || kind == K_FIXED2) return launch_fixed(kind, variant, fl, grid, threads, smem, sl.stream, kp);
+        return plan.lmax12 ? launch_12(kind, variant, fl, grid, threads, smem, sl.stream, kp)
+                           : launch_32(kind, variant, fl, grid, threads, smem, sl.stream, kp);
     };
 
-    CUDA_TRY(cudaMemsetAsync(sl.misc.p, 0, 512, sl.stream));
-    CUDA_TRY(cudaMemsetAsync(sl.lb.p, 0, n_frames * 8, sl.stream));
+    CUDA_TRY(cudaMemsetAsync(dmeta + o_misc, 0, o_lb + n_frames * 8 - o_misc, sl.stream)); /* counters, statuses, look-back words */
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
-    sl.staged = plan.staged;
+    sl.staged = !plan.staged ? 0 : stage_times ? 1 : 2;
     if (plan.staged) {
         EncParams pa = p;
         pa.lay = make_layout_front(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.front.threads,
                                    plan.front.all_planes);
         pa.all_planes = plan.front.all_planes;
         CUDA_TRY(launch(K_ANALYSE, plan.front.variant, plan.front.threads, pa.lay.total, pa));
-        CUDA_TRY(cudaEventRecord(sl.ev_s[0], sl.stream));
+        if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[0], sl.stream));
         const int wpb = 4; /* subframes (warps) per CTA of stage B */
         const size_t smem_b = (size_t)wpb * p.pre_stride;
         EncParams pb = p;
         pb.lay = lay_rec;
         CUDA_TRY(cudaFuncSetAttribute(lpc_coefficients_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-        lpc_coefficients_kernel<<<(unsigned)((n_sub + wpb - 1) / wpb), wpb * 32, smem_b, sl.stream>>>(pb, (uint32_t)n_sub);
-        CUDA_TRY(cudaGetLastError());
+        if (pdl) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)((n_sub + wpb - 1) / wpb), 1, 1);
+            cfg.blockDim = dim3(wpb * 32, 1, 1);
+            cfg.dynamicSmemBytes = smem_b;
+            cfg.stream = sl.stream;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr.val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, lpc_coefficients_kernel, pb, (uint32_t)n_sub));
+        } else {
+            lpc_coefficients_kernel<<<(unsigned)((n_sub + wpb - 1) / wpb), wpb * 32, smem_b, sl.stream>>>(pb, (uint32_t)n_sub);
+            CUDA_TRY(cudaGetLastError());
+        }
         g_launches++;
-        CUDA_TRY(cudaEventRecord(sl.ev_s[1], sl.stream));
+        if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[1], sl.stream));
         EncParams pc = p;
         pc.lay = make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.choose.threads,
                                     plan.choose.all_planes);
         pc.all_planes = plan.choose.all_planes;
         CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
-        CUDA_TRY(cudaEventRecord(sl.ev_s[2], sl.stream));
+        if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[2], sl.stream));
     }
     if (plan.ser2) {
         p.slay = plan.slay;
@@ -598,14 +622,12 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     CUDA_TRY(cudaEventRecord(sl.ev_k1, sl.stream));
 
     uint8_t *h = (uint8_t *)sl.h_meta.p;
-    meta.h_frame_off = (u64 *)h;
-    meta.h_stats = (u64 *)(h + (n_frames + 1) * 8);
-    meta.h_status = (int32_t *)(h + (n_frames + 1) * 8 + 256);
+    meta.h_frame_off = (u64 *)(h + o_foff);
+    meta.h_stats = (u64 *)(h + o_misc + 64);
+    meta.h_status = (int32_t *)(h + o_status);
     meta.threads = plan.ser2 ? plan.ser_threads : B;
     meta.smem = plan.ser2 ? (int)plan.slay.total : (int)lay.total;
-    CUDA_TRY(cudaMemcpyAsync(meta.h_frame_off, sl.frame_off.p, (n_frames + 1) * 8, cudaMemcpyDeviceToHost, sl.stream));
-    CUDA_TRY(cudaMemcpyAsync(meta.h_stats, p.stats, 256, cudaMemcpyDeviceToHost, sl.stream));
-    CUDA_TRY(cudaMemcpyAsync(meta.h_status, sl.status.p, n_frames * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CUDA_TRY(cudaMemcpyAsync(h, dmeta, meta_bytes, cudaMemcpyDeviceToHost, sl.stream));
     return FLACB_OK;
 }
 
@@ -751,13 +773,13 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
             cudaEventElapsedTime(&b0, c->ev_c0, sl.ev_k0), cudaEventElapsedTime(&b1, c->ev_c0, sl.ev_k1);
             fprintf(stderr, "chunk f0=%llu slot %d: h2d %.3f-%.3f kernels %.3f-%.3f\n", (unsigned long long)pd.f0, s, a0, a1, b0, b1);
         }
-        if (sl.staged) {
+        if (sl.staged == 1) {
             cudaEvent_t ev[5] = {sl.ev_k0, sl.ev_s[0], sl.ev_s[1], sl.ev_s[2], sl.ev_k1};
             for (int k = 0; k < 4; k++) {
                 CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
                 stage_ms[k] += ms;
             }
-        } else {
+        } else if (sl.staged == 0) {
             stage_ms[3] += ms;
         }
         if (host_in) {

@@ -53,6 +53,20 @@ namespace flacb {
 typedef unsigned long long u64;
 typedef long long i64;
 
+/* Programmatic dependent launch (sm_90+): the stages of an encode follow one another on one stream;
+ * a stage lets the next one start its CTAs as soon as all of its own are running
+ * (pdl_launch_dependents), and the next one does what does not depend on its predecessor -- taking
+ * a frame, loading and splitting its PCM -- before it waits for the predecessor's results
+ * (pdl_wait: the whole predecessor grid is complete and its memory visible).  The ragged end of
+ * one stage overlaps the start of the next.  Without the launch attribute both are no-ops. */
+#if defined(FLACB_CPU_SIM) || defined(FLACB_HOST_ONLY)
+static inline void pdl_wait() {}
+static inline void pdl_launch_dependents() {}
+#else
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 constexpr int E = 8;            /* consecutive samples per thread per tile */
 constexpr int GUARD = 64;       /* zero history in front of every channel plane (a multiple of 16: keeps the swizzle phase) */
 constexpr int TAILPAD = 48;     /* zero samples behind a plane (window reads run past the end) */
@@ -1924,6 +1938,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
     b.warp = b.tid >> 5;
     b.nwarps = b.B >> 5;
     const uint32_t f = blockIdx.x;
+    pdl_launch_dependents(); /* stage B's CTAs may come in behind this stage's last ones */
     if (b.tid == 0) {
         sh.frame = f;
 #ifdef FLACB_PHASE_TIMING
@@ -1989,6 +2004,11 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
     b.xwords = lay.xwords;
     b.red = (u64 *)(smem + lay.red);
     b.ldL = lpc_row_stride(p.L);
+    pdl_launch_dependents();
+    __syncthreads(); /* sh.frame */
+    /* the frame's PCM does not depend on the stages in front: it is split while they finish */
+    if (lay.xs_all) load_planes(b, -1);
+    pdl_wait();
     /* the records of this frame's subframes (autocorrelation only for the introspection record) */
     for (int c = 0; c < p.channels; c++) {
         const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
@@ -2019,8 +2039,7 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
             ((uint32_t *)(q + lay.o_ldc))[r] = w;
         }
     }
-    if (lay.xs_all) load_planes(b, -1);
-    else __syncthreads();
+    __syncthreads();
     for (int c = 0; c < p.channels; c++) {
         if (!lay.xs_all) load_planes(b, c);
         bind_lpc_record(b, smem + lay.lpc + (uint32_t)c * lay.lpc_stride, lay, p.L);
@@ -2052,6 +2071,8 @@ __global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p
     b.ldL = lpc_row_stride(p.L);
     const SmemLayout &lay = p.lay;
     const uint32_t s = blockIdx.x * (uint32_t)b.nwarps + (uint32_t)b.warp;
+    pdl_launch_dependents();
+    pdl_wait(); /* the autocorrelation of stage A */
     if (s >= n_sub) return;
     uint32_t *rec = (uint32_t *)(p.pre + (u64)s * (u64)p.pre_stride);
     uint32_t *loc = (uint32_t *)(smem + (uint32_t)b.warp * p.pre_stride);
@@ -2135,6 +2156,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     if (lay.xs_all) load_planes(b, -1);
     if constexpr (CHOSEN) {
         /* LPC configurations: the choice of every subframe was made by choose_kernel */
+        pdl_wait();
         for (uint32_t i = (uint32_t)b.tid; i < (uint32_t)p.channels * (sizeof(Decision) / 4); i += (uint32_t)b.B) {
             const uint32_t c = i / (uint32_t)(sizeof(Decision) / 4), k = i - c * (uint32_t)(sizeof(Decision) / 4);
             ((uint32_t *)&sh.dec[c])[k] = ((const uint32_t *)&p.dec[(u64)f * (u64)p.channels + c].d)[k];

@@ -920,7 +920,9 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
     load_planes_v2(p.pcm + (u64)f * (u64)p.block_size * (u64)p.channels * (u64)p.cbytes, b.planes, b.pstride, lay.xwords, n,
                    p.channels, p.cbytes, b.tid, b.B);
     if constexpr (CHOSEN) {
-        /* LPC configurations: the choice of every subframe was made by choose_kernel */
+        /* LPC configurations: the choice of every subframe was made by choose_kernel.  Everything up to
+         * here (ticket, tables, the frame's PCM) did not need it: see pdl_wait in flacb200_kernels.cuh */
+        pdl_wait();
         for (uint32_t i = (uint32_t)b.tid; i < (uint32_t)p.channels * (sizeof(Decision) / 4); i += (uint32_t)b.B) {
             const uint32_t c = i / (uint32_t)(sizeof(Decision) / 4), k = i - c * (uint32_t)(sizeof(Decision) / 4);
             ((uint32_t *)&sh.dec[c])[k] = ((const uint32_t *)&p.dec[(u64)f * (u64)p.channels + c].d)[k];

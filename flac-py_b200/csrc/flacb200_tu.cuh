@@ -4,6 +4,7 @@
  * launchers (flacb200_launch.h).
  */
 #define FLACB_TU_KERNELS_ONLY 1
+#include <string.h>
 #include "flacb200_launch.h"
 #include "flacb200_serialise.cuh"
 
@@ -17,11 +18,29 @@ namespace flacb {
 #define FLACB_TU_NAME fixed
 #endif
 
+/* flavour bit 8: launch with programmatic stream serialisation (the kernel may start while the kernel
+ * in front of it on the stream is still finishing; it calls pdl_wait() before it reads that kernel's results) */
+static bool g_pdl = false;
+
 template <class K>
 static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem, cudaStream_t stream, const EncParams &p)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (g_pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3((unsigned)threads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    }
     kernel<<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -29,7 +48,8 @@ static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem,
 cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour, unsigned grid, int threads, size_t smem,
                                                cudaStream_t stream, const EncParams &p)
 {
-    (void)flavour;
+    g_pdl = (flavour & 0x100) != 0;
+    flavour &= 0xFF;
 #if FLACB_TU_LMAX
     constexpr int LM = FLACB_TU_LMAX;
     switch (kind) {

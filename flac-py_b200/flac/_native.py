@@ -23,6 +23,7 @@ OUTPUT_ON_DEVICE = 0x04
 LENIENT = 0x08
 SLOT_COMPACT = 0x10
 PCM_INT32 = 0x20
+STAGE_TIMES = 0x40  # time every stage on its own (stats.stage_ms) instead of overlapping them
 
 MAX_LPC = 32
 INFO_PARAMS = 64

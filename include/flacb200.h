@@ -57,6 +57,11 @@ enum {
 #define FLACB_PCM_INT32       0x20u /* samples are int32 containers (whatever `bits` is); default
                                        is the WAV payload layout, ceil(bits/8) LE bytes/sample    */
 
+#define FLACB_STAGE_TIMES     0x40u /* time every stage of an LPC encode on its own (flacb_stats.stage_ms);
+                                       without it the stages are launched back to back with programmatic
+                                       dependent launch, the start of one overlapping the end of the one in
+                                       front, and stage_ms is left at zero                                   */
+
 #define FLACB_MAX_LPC 32
 #define FLACB_INFO_PARAMS 64
 

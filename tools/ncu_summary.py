@@ -30,7 +30,10 @@ RAW = [
 
 
 def ncu(*args):
-    return subprocess.run(["ncu", *args], capture_output=True, text=True).stdout
+    # NCU_SUMMARY_KERNEL: regular expression that picks one kernel of a report with several
+    k = os.environ.get("NCU_SUMMARY_KERNEL")
+    extra = ["-k", "regex:" + k] if k else []
+    return subprocess.run(["ncu", *extra, *args], capture_output=True, text=True).stdout
 
 
 def main():

@@ -48,6 +48,7 @@ def main():
             N.raise_for_status(rc)
             if k >= 2:
                 ks.append(st.kernel_ms)
+        rc, out_len, st = ctx.encode_raw(d_in, *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT | N.STAGE_TIMES, d_out, cap)
         ms = float(np.median(ks))
         print(json.dumps({"workload": args.workload, "shape": t, "threads": st.threads_per_frame, "smem": st.smem_bytes,
                           "kernel_ms": round(ms, 4), "stages_ms": [round(float(v), 4) for v in st.stage_ms], "Msamples/s": round(n * ch / ms / 1e3, 1),
@@ -62,6 +63,7 @@ def main():
             N.raise_for_status(rc)
             if k >= 2:
                 ks.append(st.kernel_ms)
+        rc, out_len, st = ctx.encode_raw(d_in, *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT | N.STAGE_TIMES, d_out, cap)
         ms = float(np.median(ks))
         chk = np.empty(1024, dtype=np.int32)
         ctx.d2h(chk.ctypes.data, d_pcm, 4096)
