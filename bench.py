@@ -25,7 +25,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.join(ROOT, "flac-py_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "flac-py_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools", "synth")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -38,10 +38,10 @@ WORKLOADS = {
            2, 16, 44100, 600, 4608, 12, 5, 0, 5, 0xF1AC0002),
     "c2fixed": ("16-bit stereo 44.1 kHz 10 min, block 4608, fixed predictors only, Rice partition order 0..5",
                 2, 16, 44100, 600, 4608, 0, 5, 0, 5, 0xF1AC0002),
-    "c3": ("24-bit stereo 96 kHz 10 min slice of the 1 h stream, block 16384, max LPC order 32, Rice partition order 0..8",
-           2, 24, 96000, 600, 16384, 32, 5, 0, 8, 0xF1AC0003),
-    "c4": ("24-bit 8-channel 48 kHz 5 min slice of the 10 h corpus, block 4608, max LPC order 12, Rice partition order 0..5",
-           8, 24, 48000, 300, 4608, 12, 5, 0, 5, 0xF1AC0004),
+    "c3": ("24-bit stereo 96 kHz 1 h, block 16384, max LPC order 32, qlp precision 5, Rice partition order 0..8",
+           2, 24, 96000, 3600, 16384, 32, 5, 0, 8, 0xF1AC0003),
+    "c4": ("24-bit 8-channel 48 kHz 10 h corpus (375 000 frames, 41.5 GB of PCM), block 4608, max LPC order 12, qlp precision 5, "
+           "Rice partition order 0..5", 8, 24, 48000, 36000, 4608, 12, 5, 0, 5, 0xF1AC0004),
 }
 
 
@@ -58,6 +58,21 @@ def synth(name: str, rank: int = 0, seconds: float | None = None) -> tuple[np.nd
     raw = np.frombuffer(b"".join(parts), dtype=np.uint8)
     meta = dict(desc=desc, channels=ch, bits=bits, rate=rate, n=n, block=bs, L=L, q=q, rmin=rmin, rmax=rmax)
     return raw, meta
+
+
+def workload_shape(name: str, seconds: float | None = None) -> dict:
+    desc, ch, bits, rate, secs, bs, L, q, rmin, rmax, seed = WORKLOADS[name]
+    if seconds is not None:
+        secs = seconds
+    return dict(desc=desc, channels=ch, bits=bits, rate=rate, n=int(rate * secs), block=bs, L=L, q=q, rmin=rmin, rmax=rmax, seed=seed)
+
+
+def synth_device(device: int, dst_ptr: int, name: str, start: int, n: int) -> int:
+    """The workload's PCM, sample frames [start, start + n), written by the GPU itself into its HBM
+    (tools/synth/flacb200_synth.cu: bit for bit what synth() returns; tests/test_synth_device.py)."""
+    import flacb200_synth as S
+    desc, ch, bits, rate, secs, bs, L, q, rmin, rmax, seed = WORKLOADS[name]
+    return S.pcm_device(device, dst_ptr, n, ch, bits, rate, "mixed", seed, start)
 
 
 class ClockSampler:
@@ -190,7 +205,7 @@ def oracle_in_domain(x, bits, bs, L, q, rmin, rmax, **kw):
         return O.encode_frames(x[:k * bs], bits, bs, L, q, rmin, rmax, **kw), k
 
 
-def parity_check(ctx, N, name: str, rank: int, raw: np.ndarray, m: dict, d_in: int, d_out: int, cap: int, enc_args: tuple,
+def parity_check(ctx, N, name: str, start: int, first_frame: int, n: int, d_in: int, d_out: int, cap: int, enc_args: tuple,
                  oracle_enc=None, oracle_frames: int = 0, info_frames: int = 48) -> dict:
     """The stream this rank's GPU produced against the CPU oracle, on the same PCM:
     * bytes of the first `oracle_frames` frames (the slice the CPU arm encoded anyway; a smaller slice
@@ -202,16 +217,15 @@ def parity_check(ctx, N, name: str, rank: int, raw: np.ndarray, m: dict, d_in: i
     import oracle as O
     import flacb200_synth as S
     desc, ch, bits, rate, secs, bs, L, q, rmin, rmax, seed = WORKLOADS[name]
-    n = m["n"]
     nfr = (n + bs - 1) // bs
     offs = np.zeros(nfr + 1, dtype=np.uint64)
     flags = N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT
     rc, out_len, st = ctx.encode_raw(d_in, *enc_args, flags, d_out, cap, frame_offsets=offs)
     N.raise_for_status(rc, "encode (parity)")
-    if oracle_enc is None or rank != 0:
+    if oracle_enc is None:
         oracle_frames = min(nfr, 64)
-        x = S.pcm(min(n, bs * oracle_frames), ch, bits, rate, "mixed", seed, start=rank * n)
-        oracle_enc, oracle_frames = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=rank * nfr,
+        x = S.pcm(min(n, bs * oracle_frames), ch, bits, rate, "mixed", seed, start=start)
+        oracle_enc, oracle_frames = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=first_frame,
                                                      threads=os.cpu_count() or 1)
     k = min(oracle_frames, nfr)
     want = np.frombuffer(oracle_enc.data, dtype=np.uint8)[:int(oracle_enc.frame_offsets[k])]
@@ -227,8 +241,8 @@ def parity_check(ctx, N, name: str, rank: int, raw: np.ndarray, m: dict, d_in: i
     kf = min(info_frames, nfr)
     ns = min(n, kf * bs)
     if L > 0 and kf > 0:
-        x = S.pcm(ns, ch, bits, rate, "mixed", seed, start=rank * n)
-        ref, kf = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=rank * nfr, want_info=True)
+        x = S.pcm(ns, ch, bits, rate, "mixed", seed, start=start)
+        ref, kf = oracle_in_domain(x, bits, bs, L, q, rmin, rmax, first_frame_number=first_frame, want_info=True)
         ns = min(ns, kf * bs)
         info = (N.SubframeInfo * max(kf * ch, 1))()
         if kf:
@@ -257,6 +271,61 @@ def parity_check(ctx, N, name: str, rank: int, raw: np.ndarray, m: dict, d_in: i
     return out
 
 
+def c4_strong(ctx, N, rank: int, world: int, local_rank: int, barrier, steps: int = 2) -> dict:
+    """BASELINE.json config 4 as it is stated: the 8-channel 24-bit 48 kHz 10 h corpus (375 000 frames of
+    4608, 41.5 GB of PCM), frame-sharded over the ranks -- STRONG scaling: rank r generates frames
+    [r F / N, (r + 1) F / N) on its own GPU and encodes them with their global frame numbers; no data
+    moves between ranks (the streams concatenate: `shard_check`).  Device-resident, like `value`."""
+    import torch
+    import torch.distributed as dist
+    desc, ch, bits, rate, secs, bs, L, q, rmin, rmax, seed = WORKLOADS["c4"]
+    F = rate * secs // bs
+    f0, f1 = F * rank // world, F * (rank + 1) // world
+    nfr, n = f1 - f0, (f1 - f0) * bs
+    nbytes = n * ch * 3
+    cap = N.encode_bound(n, ch, bits, bs, rmax)
+    d_in, d_out = ctx.device_alloc(nbytes), ctx.device_alloc(cap)
+    try:
+        t0 = time.perf_counter()
+        synth_device(local_rank, d_in, "c4", f0 * bs, n)
+        gen_s = time.perf_counter() - t0
+        enc_args = (n, ch, bits, bs, L, q, rmin, rmax, f0)
+        flags = N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT
+        rc, out_len, st = ctx.encode_raw(d_in, *enc_args, flags, d_out, cap)  # warm-up: buffers, first launch
+        N.raise_for_status(rc, "encode (c4_strong)")
+        barrier()
+        ctx.timer_begin()
+        for _ in range(steps):
+            rc, out_len, st = ctx.encode_raw(d_in, *enc_args, flags, d_out, cap)
+            N.raise_for_status(rc, "encode (c4_strong)")
+        dev_ms = ctx.timer_end() / steps
+        barrier()
+        try:
+            par = parity_check(ctx, N, "c4", f0 * bs, f0, n, d_in, d_out, cap, enc_args, info_frames=8)
+            par = {k: par[k] for k in ("frames_checked", "byte_mismatches", "lpc_lag_mismatches", "lpc_coef_mismatches", "decision_mismatches")}
+        except Exception as e:  # noqa: BLE001
+            par = {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        ctx.device_free(d_in)
+        ctx.device_free(d_out)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([float(out_len), float(st.out_of_domain), float(par.get("byte_mismatches", 1)),
+                        float(par.get("frames_checked", 0)), float(par.get("lpc_coef_mismatches", 1))], dtype=torch.float64,
+                       device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms = float(t.item())
+    samples = F * bs * ch
+    return {"workload": desc, "scaling": "strong", "n_gpus": world, "frames": int(F), "frames_per_rank": int(nfr),
+            "value": samples / ms / 1e3, "unit": "Msamples/s", "ms_per_step": ms, "realtime_x": F * bs / rate / (ms / 1e3),
+            "pcm_bytes": int(F * bs * ch * 3), "stream_bytes": int(tot[0].item()),
+            "frames_outside_reference_domain": int(tot[1].item()),
+            "parity": {"frames_checked": int(tot[3].item()), "byte_mismatches": int(tot[2].item()),
+                       "lpc_coef_mismatches": int(tot[4].item())},
+            "generated_on_device_s_rank0": gen_s, "timing": f"CUDA events, max over ranks, mean of {steps} steps, PCM and stream resident in HBM"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +336,7 @@ def main():
     ap.add_argument("--copies", type=int, default=3, help="distinct device copies rotated between steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seconds", type=float, default=None, help="override the stream length (debugging)")
+    ap.add_argument("--no-c4-strong", action="store_true", help="skip the config-4 strong-scaling record")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -325,22 +395,33 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # nvidia-smi takes about a second to come up: start it before the synthesis
-    raw, m = synth(args.workload, rank, args.seconds)
+    m = workload_shape(args.workload, args.seconds)
     ch, bits, bs = m["channels"], m["bits"], m["block"]
     n = m["n"]
+    cbytes = (bits + 7) // 8
     ctx = N.Context(local_rank)
-    pcm_bytes = raw.size
+    pcm_bytes = n * ch * cbytes
     cap = N.encode_bound(n, ch, bits, bs, m["rmax"])
-    copies = max(1, args.copies)
+    nfr = (n + bs - 1) // bs
+    # The PCM is generated on the device (rank r: sample frames [r n, (r + 1) n) of the N times longer stream).
+    # Inputs of more than 3 GiB (config 4: 41.5 GB) get one device copy (they are far larger than L2 anyway) and
+    # no host copy: their end-to-end leg runs on the first GiB of PCM.
+    big = pcm_bytes > (3 << 30)
+    copies = 1 if big else max(1, args.copies)
     d_in = [ctx.device_alloc(pcm_bytes) for _ in range(copies)]
     d_out = [ctx.device_alloc(cap) for _ in range(copies)]
-    pin_in = N.PinnedBuffer(pcm_bytes)
-    pin_in.array[:] = raw
-    pin_out = N.PinnedBuffer(cap)
     for d in d_in:
-        ctx.h2d(d, pin_in.ptr, pcm_bytes)
-    nfr = (n + bs - 1) // bs
+        synth_device(local_rank, d, args.workload, rank * n, n)
+    e2e_frames = nfr if not big else max(1, (1 << 30) // (bs * ch * cbytes))
+    e2e_n = n if not big else e2e_frames * bs
+    e2e_bytes = e2e_n * ch * cbytes
+    e2e_cap = N.encode_bound(e2e_n, ch, bits, bs, m["rmax"])
+    pin_in = N.PinnedBuffer(e2e_bytes)
+    ctx.d2h(pin_in.ptr, d_in[0], e2e_bytes)
+    raw = pin_in.array  # the (first GiB of the) PCM on the host
+    pin_out = N.PinnedBuffer(e2e_cap)
     enc_args = (n, ch, bits, bs, m["L"], m["q"], m["rmin"], m["rmax"], rank * nfr)
+    e2e_args = (e2e_n,) + enc_args[1:]
 
     def step_resident(k: int, extra_flags: int = 0):
         rc, out_len, st = ctx.encode_raw(d_in[k % copies], *enc_args, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT | extra_flags,
@@ -349,7 +430,7 @@ def main():
         return out_len, st
 
     def step_e2e():
-        rc, out_len, st = ctx.encode_raw(pin_in.ptr, *enc_args, N.LENIENT, pin_out.ptr, cap)
+        rc, out_len, st = ctx.encode_raw(pin_in.ptr, *e2e_args, N.LENIENT, pin_out.ptr, e2e_cap)
         N.raise_for_status(rc, "encode (host buffers)")
         return out_len, st
 
@@ -392,7 +473,7 @@ def main():
     ctx.sync()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    assert e_len == flac_bytes
+    assert big or e_len == flac_bytes
 
     # ---- the CPU arm (rank 0, one GPU): the oracle port on a bounded slice of the same PCM; its bytes are
     # the reference for the parity check below ----
@@ -403,8 +484,9 @@ def main():
     # ---- parity of the benchmarked stream itself (every rank checks its own frame range) ----
     last = (args.warmup + args.steps - 1) % copies
     try:
-        parity = parity_check(ctx, N, args.workload, rank, raw, m, d_in[last], d_out[last], cap, enc_args,
-                              cb_arm["_enc"] if cb_arm else None, cb_arm["_frames"] if cb_arm else 0)
+        parity = parity_check(ctx, N, args.workload, rank * n, rank * nfr, n, d_in[last], d_out[last], cap, enc_args,
+                              cb_arm["_enc"] if cb_arm else None, cb_arm["_frames"] if cb_arm else 0,
+                              info_frames=48 if bs <= 8192 else 12)
     except Exception as e:  # noqa: BLE001
         parity = {"error": f"{type(e).__name__}: {e}"}
     shard_check = None
@@ -420,9 +502,7 @@ def main():
             # single GPU gives for that range (frame numbers included), so the ranks' streams concatenate to the
             # single stream
             r = world - 1
-            raw_r, _ = synth(args.workload, r, args.seconds)
-            pin_in.array[:] = raw_r
-            ctx.h2d(d_in[0], pin_in.ptr, pcm_bytes)
+            synth_device(local_rank, d_in[0], args.workload, r * n, n)
             rc, len_r, _ = ctx.encode_raw(d_in[0], *enc_args[:-1], r * nfr, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE | N.LENIENT, d_out[0], cap)
             N.raise_for_status(rc, "encode (shard check)")
             other = np.empty(len_r, dtype=np.uint8)
@@ -442,7 +522,7 @@ def main():
     # ---- config 5 on the side (rank 0, stereo streams: the reference decoder's domain): decode the stream
     # just produced back to PCM; the WHOLE result is compared with the input; not part of `value` ----
     decode_info = None
-    if rank == 0 and ch == 2:
+    if rank == 0 and ch == 2 and not big:
         try:
             import oracle as O
             pcm_cap = n * ch + 1024
@@ -452,7 +532,6 @@ def main():
                 rc, nsf, fch, dst = ctx.decode_raw(d_out[last], flac_bytes, bits, N.INPUT_ON_DEVICE | N.OUTPUT_ON_DEVICE, d_pcm, pcm_cap)
                 N.raise_for_status(rc, "decode (resident)")
                 dms.append(dst.kernel_ms)
-            cbytes = (bits + 7) // 8
             src = raw.reshape(-1, cbytes).astype(np.int32)
             want = src[:, 0] | (src[:, 1] << 8) | ((src[:, 2] << 16) if cbytes == 3 else 0)
             want = (want ^ (1 << (8 * cbytes - 1))) - (1 << (8 * cbytes - 1))
@@ -491,6 +570,14 @@ def main():
         except Exception as e:  # noqa: BLE001  (never fail the encode bench over the side measurement)
             decode_info = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- BASELINE.json config 4, strong scaling over the ranks (a record of its own on the default line) ----
+    c4_info = None
+    if args.workload == "c2" and not args.no_c4_strong and args.seconds is None:
+        try:
+            c4_info = c4_strong(ctx, N, rank, world, local_rank, barrier)
+        except Exception as e:  # noqa: BLE001
+            c4_info = {"error": f"{type(e).__name__}: {e}"}
+
     # max over ranks of the device time; totals over ranks
     t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -498,7 +585,7 @@ def main():
     dev_ms, e2e_ms, wall_ms = (float(v) for v in t.tolist())
     samples_per_step = n * ch * world
     value = samples_per_step * args.steps / (dev_ms / 1e3) / 1e6
-    e2e_value = samples_per_step * e2e_steps / (e2e_ms / 1e3) / 1e6
+    e2e_value = e2e_n * ch * world * e2e_steps / (e2e_ms / 1e3) / 1e6
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -517,8 +604,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32/int64 + f64 (LPC analysis)", "data": "synthetic",
             "config": {"workload": desc, "samples_per_step_per_gpu": n * ch, "frames_per_step_per_gpu": nfr,
-                       "l2": f"{copies} distinct device copies of input and output rotated between steps "
+                       "l2": f"{copies} distinct device cop{'ies' if copies > 1 else 'y'} of input and output rotated between steps "
                              f"({copies * (pcm_bytes + cap) / 1e6:.0f} MB > 126 MB L2)",
+                       "data_generated": "on the device (tools/synth/flacb200_synth.cu), bit-identical to the numpy generator",
                        "sharding": "frame ranges, one rank per GPU, no data-path collective",
                        "host_binding_rank0": host_binding,
                        "threads_per_frame": st.threads_per_frame, "smem_bytes_per_frame": st.smem_bytes},
@@ -537,14 +625,17 @@ def main():
                          "note": "dominant kernel of the step (CUDA events around each stage on the launching stream); "
                                  "pipeline = all stages of the step together.  LPC configs are integer/fp64-ALU bound by "
                                  "the reference's semantics (all orders 1..L evaluated on every sample): see DESIGN.md"},
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(pcm_bytes * world),
-                    "d2h_bytes_per_step": int(flac_bytes * world), "ms_per_step": e2e_ms / e2e_steps,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(e2e_bytes * world),
+                    "d2h_bytes_per_step": int(e_len * world), "ms_per_step": e2e_ms / e2e_steps,
+                    "sample": "the whole workload" if not big else f"the first {e2e_frames} frames ({e2e_bytes / 1e9:.2f} GB of PCM) of the workload",
                     "h2d_ms": e_st.h2d_ms, "kernel_ms": e_st.kernel_ms, "d2h_ms": e_st.d2h_ms,
                     "realtime_x": e2e_value * 1e6 / (m["rate"] * ch)},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "decode": decode_info,
         }
         if shard_check is not None:
             line["shard_check"] = shard_check
+        if c4_info is not None:
+            line["c4_strong"] = c4_info
         line["cpu_baseline"] = {k: cb_arm[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb_arm else None
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

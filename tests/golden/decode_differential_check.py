@@ -20,7 +20,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path[:0] = [os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'flac-py_b200')]
+sys.path[:0] = [os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'flac-py_b200'), os.path.join(ROOT, 'tools', 'synth')]
 import numpy as np, oracle as O, refharness as R, flacb200_synth as S, simlib
 STATUS={0:None,1:"AssertionError",2:"ValueError",3:"ZeroDivisionError",4:"EOFError",6:"OverflowError",7:"KeyError"}
 rng=random.Random(int(sys.argv[2]) if len(sys.argv)>2 else 1)

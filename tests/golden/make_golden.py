@@ -6,7 +6,7 @@ Run in the build container, where the reference is mounted at /root/reference:
     python tests/golden/make_golden.py
 
 For each case the unmodified reference encoder (flac/encoder.py:48 encode) is run on
-deterministic synthetic PCM (flac-py_b200/flacb200_synth.py) and the following is
+deterministic synthetic PCM (tools/synth/flacb200_synth.py) and the following is
 stored under tests/golden/:
 
     cases.json          parameters, sha256 of PCM and of the reference stream, frame chunk
@@ -32,6 +32,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "flac-py_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
 
 import numpy as np  # noqa: E402
 

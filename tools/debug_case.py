@@ -4,7 +4,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [os.path.join(ROOT, "flac-py_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), ROOT]
+sys.path[:0] = [os.path.join(ROOT, "flac-py_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools", "synth"), ROOT]
 import numpy as np  # noqa: E402
 import flacb200_synth as S  # noqa: E402
 import oracle as O  # noqa: E402

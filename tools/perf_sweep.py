@@ -10,7 +10,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [os.path.join(ROOT, "flac-py_b200"), ROOT]
+sys.path[:0] = [os.path.join(ROOT, "flac-py_b200"), os.path.join(ROOT, "tools", "synth"), ROOT]
 import numpy as np  # noqa: E402
 
 import bench  # noqa: E402
@@ -26,15 +26,18 @@ def main():
     ap.add_argument("--decode", action="store_true")
     ap.add_argument("--slots", action="store_true", help="slot + compaction placement instead of look-back")
     args = ap.parse_args()
-    raw, m = bench.synth(args.workload, 0, args.seconds)
+    m = bench.workload_shape(args.workload, args.seconds)
     ctx = N.Context(0)
     n, ch, bits, bs = m["n"], m["channels"], m["bits"], m["block"]
+    nbytes = n * ch * ((bits + 7) // 8)
     cap = N.encode_bound(n, ch, bits, bs, m["rmax"])
-    d_in = ctx.device_alloc(raw.size)
+    d_in = ctx.device_alloc(nbytes)
     d_out = ctx.device_alloc(cap)
-    pin = N.PinnedBuffer(raw.size)
-    pin.array[:] = raw
-    ctx.h2d(d_in, pin.ptr, raw.size)
+    bench.synth_device(0, d_in, args.workload, 0, n)
+
+    class _Raw:
+        size = nbytes
+    raw = _Raw()
     enc_args = (n, ch, bits, bs, m["L"], m["q"], m["rmin"], m["rmax"], 0)
     out_len = 0
     for t in args.threads.split(";"):  # "0" = library default, else "threads,all_planes,variant"

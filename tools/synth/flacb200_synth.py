@@ -15,7 +15,7 @@ silence, no DC, every Rice partition has mean zig-zag >= 1.
     highpass  same with rho = -0.9
     white     near-white gaussian-ish noise, sigma about full-scale / 8
               (the only class on which the reference picks SubframeLPC)
-    silence   dither only, uniform in [-3, 3]
+    silence   dither only, uniform in [-3, 3] at the 16-bit level
     clip      sine at +6 dB over full scale, hard clipped, then re-dithered
 
 `mixed` cycles through the six classes in segments of SEGMENT sample frames.
@@ -112,7 +112,17 @@ def _class_samples(cls: str, idx: np.ndarray, ch: int, bits: int, rate: int, see
     if cls == "white":
         return _gauss(seed, st + 3, idx, fs // 8)
     if cls == "silence":
-        return _uniform(seed, st + 4, idx, -3, 3)
+        # Dither only, +-3 LSB at the 16-bit level.  For wider samples it is two-tap shaped dither at that
+        # level: on WHITE low-level noise the reference's best LPC order and its best fixed predictor give
+        # sums of |residual| that differ by a short random walk, and they tie -- the reference's
+        # `assert False`, encoder.py:157 -- about once in 3 000 subframes (measured: 151 frames of the
+        # 375 000 of config 4, 3 of config 3's 21 094).  With a little correlation the (sign-inverted) LPC
+        # predictor loses by a margin and the long 24-bit corpora stay inside the reference's domain.
+        if bits <= 16:
+            return _uniform(seed, st + 4, idx, -3, 3)
+        d = 3 << (bits - 16)
+        prev = np.where(idx >= 1, _uniform(seed, st + 4, np.maximum(idx - 1, 0), -d, d), 0)
+        return _uniform(seed, st + 4, idx, -d, d) + prev
     if cls == "clip":
         f = 1000 + 100 * ch if bits <= 16 else 1500 + 100 * ch
         step = (f << 32) // rate
@@ -177,3 +187,47 @@ def unpack_le(data: bytes, channels: int, bits: int) -> np.ndarray:
     else:
         raise ValueError(f"unsupported sample size {bits}")
     return a.reshape(-1, channels)
+
+
+# ---- the same generator on the device (tools/synth/flacb200_synth.cu): benchmark corpora that no host
+# could hold or produce in time are written straight into HBM, bit for bit what pcm() returns ----
+_dev_lib = None
+_dev_lut_set = set()
+
+
+def device_lib():
+    import ctypes as C
+    import os
+    import subprocess
+    global _dev_lib
+    if _dev_lib is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "libflacb200_synth.so")
+        src = os.path.join(here, "flacb200_synth.cu")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.run(["make", "-C", here, "-B", "libflacb200_synth.so"], check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.flacb_synth_set_lut.restype = C.c_int
+        L.flacb_synth_set_lut.argtypes = [C.c_int, C.c_void_p]
+        L.flacb_synth_pcm.restype = C.c_int
+        L.flacb_synth_pcm.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]
+        _dev_lib = L
+    return _dev_lib
+
+
+def pcm_device(device: int, dst_ptr: int, n: int, channels: int, bits: int = 16, rate: int = 44100, cls: str = "mixed",
+               seed: int = 0xF1AC0000, start: int = 0) -> int:
+    """Write pack_le(pcm(n, channels, bits, rate, cls, seed, start), bits) to device memory at dst_ptr
+    (a pointer on CUDA device `device`); returns the number of bytes written."""
+    L = device_lib()
+    if device not in _dev_lut_set:
+        lut = np.ascontiguousarray(_sine_lut(), dtype=np.int64)
+        rc = L.flacb_synth_set_lut(device, lut.ctypes.data)
+        if rc:
+            raise RuntimeError(f"flacb_synth_set_lut failed ({rc})")
+        _dev_lut_set.add(device)
+    k = 6 if cls == "mixed" else CLASSES.index(cls)
+    rc = L.flacb_synth_pcm(device, dst_ptr, start, n, channels, bits, rate, k, seed & 0xFFFFFFFFFFFFFFFF)
+    if rc:
+        raise RuntimeError(f"flacb_synth_pcm failed ({rc})")
+    return n * channels * ((bits + 7) // 8)
