@@ -271,6 +271,104 @@ def parity_check(ctx, N, name: str, start: int, first_frame: int, n: int, d_in: 
     return out
 
 
+def api_and_cli(name: str, m: dict, raw: np.ndarray, flac_bytes: int) -> dict:
+    """`e2e_api`: bytes in -> b"".join(flac.encoder.encode_pcm(...)) -> bytes out, the drop-in's bulk entry
+    (what the command line calls); `cli`: `python -m flac encode / decode` on a WAV file in /dev/shm, the
+    time the tool prints (the reference's own timing line, flac/__main__.py:108-109, :54-55) and the wall
+    time of the process (interpreter start, CUDA context and library load included)."""
+    import tempfile
+    import wave
+    from flac.encoder import EncoderParameters, encode_pcm
+    ch, bits, bs, rate, n = m["channels"], m["bits"], m["block"], m["rate"], m["n"]
+    params = EncoderParameters(block_size=bs, rice_partition_order=range(m["rmin"], m["rmax"] + 1),
+                               lpc_order=range(m["L"] + 1), qlp_precision=m["q"])
+    payload = raw.tobytes()  # a Python bytes object: pageable memory, like wave.readframes() returns
+    ts, size = [], 0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        stream = b"".join(encode_pcm(rate, bits, ch, payload, params, strict=False))
+        ts.append(time.perf_counter() - t0)
+        size = len(stream)
+    dt = float(np.median(ts[1:]))
+    out = {"e2e_api": {"value": n * ch / dt / 1e6, "unit": "Msamples/s", "ms": dt * 1e3, "bytes_in": len(payload), "bytes_out": size,
+                       "stream_matches_resident_encode": bool(size == 42 + flac_bytes),
+                       "call": "b''.join(flac.encoder.encode_pcm(rate, bits, channels, payload_bytes, parameters))"}}
+    if bits == 16 and ch == 2:  # the only layout the reference's command line parses correctly (SURVEY.md 9.1)
+        tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        wav, flac, back = (os.path.join(tmp, f) for f in ("in.wav", "out.flac", "back.wav"))
+        try:
+            with wave.open(wav, "wb") as w:
+                w.setnchannels(ch), w.setsampwidth(2), w.setframerate(rate)
+                w.writeframes(payload)
+            env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "flac-py_b200"))
+            rec = {}
+            for action, a, b in (("encode", wav, flac), ("decode", flac, back)):
+                cmd = [sys.executable, "-m", "flac", action, a, b]
+                if action == "encode":
+                    cmd += ["-b", str(bs), "-l", str(m["L"]), "-q", str(m["q"]), "-r", f"{m['rmin']},{m['rmax']}"]
+                t0 = time.perf_counter()
+                r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+                wall = time.perf_counter() - t0
+                printed = [ln for ln in r.stdout.splitlines() if "completed in" in ln]
+                secs = float(printed[-1].split("completed in")[1].split()[0]) if printed else None
+                rec[action] = {"printed_s": secs, "process_wall_s": wall, "rc": r.returncode,
+                               "Msamples_per_s_printed": n * ch / secs / 1e6 if secs else None}
+            with wave.open(back, "rb") as w:
+                same = w.readframes(w.getnframes()) == payload
+            rec["flac_bytes"] = os.path.getsize(flac)
+            rec["round_trip_bit_exact"] = bool(same)
+            rec["stream_matches_resident_encode"] = bool(rec["flac_bytes"] == 42 + flac_bytes)
+            out["cli"] = rec
+        finally:
+            for f in (wav, flac, back):
+                if os.path.exists(f):
+                    os.remove(f)
+            os.rmdir(tmp)
+    return out
+
+
+def pcie_ceiling(world: int, local_rank: int, mb: int = 128, iters: int = 10) -> dict:
+    """Aggregate host<->device copy rate of THIS box with all ranks copying at the same time (pinned host
+    memory, plain copies, no kernels): H2D alone, D2H alone, both at once.  The end-to-end encode can go
+    no faster than its bytes through these (tools/pcie_concurrent_probe.py is the same thing stand-alone)."""
+    import torch
+    import torch.distributed as dist
+    n = mb << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_in.fill_(1)
+    d_a = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    d_b = torch.ones(n, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    sync_t = torch.zeros(1, device=f"cuda:{local_rank}")
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    out = {}
+    for name, fns, nbytes in (("h2d", (h2d,), n), ("d2h", (d2h,), n), ("duplex", (h2d, d2h), 2 * n)):
+        for f in fns:
+            f()
+        if world > 1:
+            dist.all_reduce(sync_t)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            for f in fns:
+                f()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = world * nbytes * iters / float(t.item()) / 1e9
+    return {"h2d_GBps": out["h2d"], "d2h_GBps": out["d2h"], "duplex_GBps": out["duplex"], "n_gpus": world,
+            "how": f"{mb} MiB pinned copies, every rank at the same time, max over ranks; aggregate over the ranks"}
+
+
 def c4_strong(ctx, N, rank: int, world: int, local_rank: int, barrier, steps: int = 2) -> dict:
     """BASELINE.json config 4 as it is stated: the 8-channel 24-bit 48 kHz 10 h corpus (375 000 frames of
     4608, 41.5 GB of PCM), frame-sharded over the ranks -- STRONG scaling: rank r generates frames
@@ -474,6 +572,19 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     assert big or e_len == flac_bytes
+    try:
+        pcie = pcie_ceiling(world, local_rank)
+    except Exception as e:  # noqa: BLE001
+        pcie = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- the path users call: the package's bulk entry with Python objects (pageable memory) on both sides,
+    # and the reference's own command line on a WAV file (rank 0, one GPU) ----
+    api_info = None
+    if rank == 0 and world == 1 and not big:
+        try:
+            api_info = api_and_cli(args.workload, m, raw, flac_bytes)
+        except Exception as e:  # noqa: BLE001
+            api_info = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- the CPU arm (rank 0, one GPU): the oracle port on a bounded slice of the same PCM; its bytes are
     # the reference for the parity check below ----
@@ -632,6 +743,23 @@ def main():
                     "realtime_x": e2e_value * 1e6 / (m["rate"] * ch)},
             "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "decode": decode_info,
         }
+        if "error" not in pcie:
+            # lower bound of an end-to-end step on this box: the PCM in and the stream out at the measured ceilings,
+            # both directions at once
+            h_ms = e2e_bytes * world / pcie["h2d_GBps"] / 1e6
+            d_ms = e_len * world / pcie["d2h_GBps"] / 1e6
+            x_ms = (e2e_bytes + e_len) * world / pcie["duplex_GBps"] / 1e6
+            bound = max(h_ms, d_ms, x_ms)
+            line["e2e"]["pcie_ceiling"] = pcie
+            line["e2e"]["pcie_bound_ms"] = bound
+            line["e2e"]["frac_of_pcie_ceiling"] = bound / (e2e_ms / e2e_steps)
+            line["e2e"]["saturates_first"] = "h2d" if h_ms >= max(d_ms, x_ms) else ("d2h" if d_ms >= x_ms else "both directions together")
+        else:
+            line["e2e"]["pcie_ceiling"] = pcie
+        if api_info is not None:
+            line.update(api_info)
+            if "e2e_api" in api_info:
+                line["e2e_api"]["frac_of_e2e"] = api_info["e2e_api"]["value"] / e2e_value
         if shard_check is not None:
             line["shard_check"] = shard_check
         if c4_info is not None:

@@ -189,9 +189,24 @@ class Context:
         self.device = device
 
     def close(self):
+        for b in getattr(self, "_staging", {}).values():
+            b.free()
+        self._staging = {}
         if self._h:
             lib().flacb_destroy(self._h)
             self._h = C.c_void_p()
+
+    def staging(self, which: str, nbytes: int) -> "PinnedBuffer":
+        """Page-locked staging memory of the context ("in" / "out"), grown on demand and reused between
+        calls: Python objects (bytes, numpy arrays) live in pageable memory, from which the copy engines
+        run at a fraction of their rate and never at the same time as the kernels."""
+        st = self.__dict__.setdefault("_staging", {})
+        b = st.get(which)
+        if b is None or b.nbytes < nbytes:
+            if b is not None:
+                b.free()
+            b = st[which] = PinnedBuffer(nbytes + nbytes // 4 + 4096)
+        return b
 
     def __del__(self):
         try:

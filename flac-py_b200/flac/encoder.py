@@ -122,7 +122,7 @@ class _Shard:
 
 
 def _run_shard(sh: _Shard, raw: np.ndarray, n_sample_frames: int, channels: int, bits: int,
-               p: EncoderParameters, first_frame_number: int, flags: int, want_info: bool):
+               p: EncoderParameters, first_frame_number: int, flags: int, want_info: bool, copy_out: bool = True):
     try:
         bs = p.block_size
         cbytes = 4 if flags & N.PCM_INT32 else (bits + 7) // 8
@@ -132,14 +132,19 @@ def _run_shard(sh: _Shard, raw: np.ndarray, n_sample_frames: int, channels: int,
         nfr = sh.f1 - sh.f0
         rmin, rmax = p.rice_partition_order.start, p.rice_partition_order.stop - 1
         cap = N.encode_bound(n, channels, bits, bs, rmax)
-        out = np.empty(cap, dtype=np.uint8)
         offs = np.zeros(nfr + 1, dtype=np.uint64)
         info = (N.SubframeInfo * max(nfr * channels, 1))() if want_info else None
         part = raw[s0 * channels * cbytes:s1 * channels * cbytes]
-        rc, out_len, st = sh.ctx.encode_raw(part.ctypes.data, n, channels, bits, bs, p.max_lpc_order,
+        # through the context's page-locked staging memory: one host copy in, and the stream is read
+        # out of page-locked memory (the library overlaps the copies of its chunks with its kernels)
+        pin_in = sh.ctx.staging("in", part.size)
+        pin_out = sh.ctx.staging("out", cap)
+        np.copyto(pin_in.array[:part.size], part)
+        rc, out_len, st = sh.ctx.encode_raw(pin_in.ptr, n, channels, bits, bs, p.max_lpc_order,
                                             p.qlp_precision, rmin, rmax, first_frame_number + sh.f0,
-                                            flags, out.ctypes.data, cap, offs, info)
-        sh.rc, sh.out, sh.offs, sh.stats, sh.info = rc, out[:out_len], offs, st, info
+                                            flags, pin_out.ptr, cap, offs, info)
+        out = pin_out.array[:out_len]
+        sh.rc, sh.out, sh.offs, sh.stats, sh.info = rc, (out.copy() if copy_out else out), offs, st, info
     except BaseException as e:  # noqa: BLE001
         sh.error = e
 
@@ -158,7 +163,7 @@ def _as_raw(pcm, channels: int, sample_size: int) -> tuple[np.ndarray, int, int]
 def encode_frames(sample_size: int, channels: int, pcm, parameters: EncoderParameters, *,
                   first_frame_number: int = 0, strict: bool = True, spec_channels: bool = False,
                   devices: Optional[Sequence[int]] = None, want_info: bool = False,
-                  flags: int = 0):
+                  flags: int = 0, copy_out: bool = True):
     """Encode the frames of `pcm` (no prologue).  Returns (data: np.uint8 array per shard list,
     frame chunks iterator helper data).  Internal building block of encode_pcm / encode."""
     raw, n, f_in = _as_raw(pcm, channels, sample_size)
@@ -176,7 +181,8 @@ def encode_frames(sample_size: int, channels: int, pcm, parameters: EncoderParam
         ctxs = [N.default_context(d) for d in devices]
     g = max(1, min(len(ctxs), nfr))
     shards = [_Shard(ctxs[k], nfr * k // g, nfr * (k + 1) // g) for k in range(g)]
-    args = (raw, n, channels, sample_size, parameters, first_frame_number, flags, want_info)
+    # copy_out=False: a shard's `out` is a view of its context's staging memory, valid until the next call
+    args = (raw, n, channels, sample_size, parameters, first_frame_number, flags, want_info, copy_out)
     if g == 1:
         _run_shard(shards[0], *args)
     else:
@@ -221,8 +227,8 @@ def encode_pcm(sample_rate: int, sample_size: int, channels: int, pcm, parameter
         m = min(per_call, n - done)
         part = raw[done * channels * cbytes:(done + m) * channels * cbytes]
         shards = encode_frames(sample_size, channels, part, parameters, first_frame_number=done // bs,
-                               strict=strict, spec_channels=spec_channels, devices=devices, flags=f_in)
-        yield from _yield_shards(shards)
+                               strict=strict, spec_channels=spec_channels, devices=devices, flags=f_in, copy_out=False)
+        yield from _yield_shards(shards)  # every frame is copied out of the staging memory here, before the next call
         done += m
 
 
