@@ -984,9 +984,17 @@ static int decode_emit(flacb_ctx *c, uint32_t flags, int32_t *pcm_out, uint64_t 
     return c->pend_dec.status;
 }
 
+/* flacb_scan_frames: where the frames of the stream are, instead of their samples */
+struct ScanOut {
+    uint64_t *offsets;      /* cap + 1 */
+    uint32_t *block_sizes;  /* cap, may be null */
+    uint64_t cap;
+    uint64_t n_frames;
+};
+
 static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits,
                               uint32_t flags, int32_t *pcm_out, uint64_t cap_samples, uint64_t *n_sample_frames,
-                              int *frame_channels, flacb_stats *stats, int check_crc8)
+                              int *frame_channels, flacb_stats *stats, int check_crc8, ScanOut *scan = nullptr)
 {
     if (n_sample_frames) *n_sample_frames = 0;
     if (frame_channels) *frame_channels = 0;
@@ -1084,6 +1092,27 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     const int fch = h_res->frame_channels;
     rc = h_res->status;
     if (rc == STATUS_CRC8_MISMATCH || rc == STATUS_DEFERRED) return STATUS_CRC8_MISMATCH; /* the chain reached a frame with a bad header CRC: caller retries unfiltered */
+    if (scan) {
+        /* the frames the reference visits, in stream order: the candidates on the chain */
+        std::vector<Candidate> h_cand(n_cand);
+        CUDA_TRY(cudaMemcpy(h_cand.data(), d_cand, n_cand * sizeof(Candidate), cudaMemcpyDeviceToHost));
+        u64 k = 0, end = 0;
+        for (u64 i = 0; i < n_cand; i++) {
+            if (!h_cand[i].on_chain) continue;
+            if (k < scan->cap) {
+                scan->offsets[k] = h_cand[i].start;
+                if (scan->block_sizes) scan->block_sizes[k] = (uint32_t)h_cand[i].bs;
+            }
+            end = h_cand[i].end;
+            k++;
+        }
+        scan->n_frames = k;
+        if (n_sample_frames) *n_sample_frames = nsf;
+        if (frame_channels) *frame_channels = fch;
+        if (k > scan->cap) return FLACB_E_NOSPACE;
+        scan->offsets[k] = end;
+        return rc;
+    }
     CUDA_TRY(cudaEventRecord(c->ev_k1, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&k_ms, c->ev_k0, c->ev_k1));
@@ -1117,6 +1146,22 @@ extern "C" int flacb_decode_frames(flacb_ctx *c, const uint8_t *frames, uint64_t
     if (rc == STATUS_CRC8_MISMATCH)
         rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, pcm_out, cap_samples, n_sample_frames,
                                 frame_channels, stats, 0);
+    return rc;
+}
+
+extern "C" int flacb_scan_frames(flacb_ctx *c, const uint8_t *frames, uint64_t len, int streaminfo_bits, uint32_t flags,
+                                 uint64_t *offsets, uint32_t *block_sizes, uint64_t cap_frames, uint64_t *n_frames,
+                                 uint64_t *n_sample_frames, int *frame_channels)
+{
+    if (n_frames) *n_frames = 0;
+    if (!c || !offsets) return FLACB_E_ASSERT;
+    ScanOut so = {offsets, block_sizes, cap_frames, 0};
+    offsets[0] = 0;
+    int rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, nullptr, 0, n_sample_frames, frame_channels, nullptr, 1, &so);
+    if (rc == STATUS_CRC8_MISMATCH)
+        rc = decode_frames_impl(c, frames, len, streaminfo_bits, flags, nullptr, 0, n_sample_frames, frame_channels, nullptr, 0, &so);
+    if (n_frames) *n_frames = so.n_frames;
+    c->pend_dec.valid = false;
     return rc;
 }
 

@@ -73,7 +73,7 @@ EXPORTS = [
     "flacb_version", "flacb_device_count", "flacb_strerror", "flacb_last_cuda_error",
     "flacb_create", "flacb_destroy", "flacb_host_alloc", "flacb_host_free", "flacb_device_alloc",
     "flacb_device_free", "flacb_memcpy_h2d", "flacb_memcpy_d2h", "flacb_encode_bound",
-    "flacb_encode_pcm", "flacb_stream_prologue", "flacb_decode_frames", "flacb_decode_output", "flacb_timer_begin",
+    "flacb_encode_pcm", "flacb_stream_prologue", "flacb_decode_frames", "flacb_decode_output", "flacb_scan_frames", "flacb_timer_begin",
     "flacb_timer_end", "flacb_sync", "flacb_kernel_launches",
 ]
 
@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
         L.flacb_decode_frames.argtypes = [vp, vp, u64, i32, u32, vp, u64, C.POINTER(u64),
                                           C.POINTER(i32), C.POINTER(Stats)]
         L.flacb_timer_begin.restype = i32
+        L.flacb_scan_frames.restype = i32
+        L.flacb_scan_frames.argtypes = [vp, vp, u64, i32, u32, vp, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
         L.flacb_decode_output.restype = i32
         L.flacb_decode_output.argtypes = [vp, u32, vp, u64, C.POINTER(u64), C.POINTER(i32), C.POINTER(Stats)]
         L.flacb_timer_begin.argtypes = [vp]
@@ -265,6 +267,16 @@ class Context:
                                        flags, C.c_void_p(out_ptr), cap_samples, C.byref(n),
                                        C.byref(fch), C.byref(st))
         return rc, n.value, fch.value, st
+
+    def scan_frames(self, frames_ptr: int, nbytes: int, streaminfo_bits: int, flags: int, cap_frames: int):
+        """-> (status, offsets uint64 [n + 1], block_sizes uint32 [n], n_sample_frames, frame_channels)"""
+        offs = np.zeros(cap_frames + 1, dtype=np.uint64)
+        sizes = np.zeros(max(cap_frames, 1), dtype=np.uint32)
+        n, ns, fch = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        rc = lib().flacb_scan_frames(self._h, C.c_void_p(frames_ptr), nbytes, streaminfo_bits, flags, offs.ctypes.data,
+                                     sizes.ctypes.data, cap_frames, C.byref(n), C.byref(ns), C.byref(fch))
+        k = min(n.value, cap_frames)
+        return rc, offs[:k + 1], sizes[:k], n.value, ns.value, fch.value
 
     def decode_output(self, flags: int, out_ptr: int, cap_samples: int):
         """After decode_raw returned E_NOSPACE: write the frames it decoded (they are still in the

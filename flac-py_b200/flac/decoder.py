@@ -61,6 +61,50 @@ def decode_frames_status(frames, sample_size: int, *, devices: Optional[Sequence
     return out[:n * fch].reshape(-1, fch), fch, rc
 
 
+def scan_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None) -> tuple[np.ndarray, np.ndarray, int, int]:
+    """The frame index of back-to-back audio frames (bytes-like): byte offsets of the frames the reference's
+    get_frames loop (decoder.py:100-108) visits plus the end of the last one, their block sizes, the number of
+    sample frames and the status the decode would end with.  Found in parallel on the GPU (every sync candidate
+    is parsed, the real frames are the chain from offset 0); the reference finds frame k by parsing 0 .. k-1."""
+    raw = np.frombuffer(frames, dtype=np.uint8) if not isinstance(frames, np.ndarray) else frames
+    ctx = N.default_context(devices[0] if devices else None)
+    cap = max(raw.size // 64, 64)
+    while True:
+        rc, offs, sizes, n, ns, _ = ctx.scan_frames(raw.ctypes.data if raw.size else 0, raw.size, sample_size, 0, cap)
+        if rc != N.E_NOSPACE:
+            break
+        cap = n
+    if rc in (N.E_CUDA, N.E_UNSUPPORTED, N.E_INTERNAL):
+        N.raise_for_status(rc, "scan")
+    return offs, sizes, ns, rc
+
+
+def frame_headers(frames, sample_size: int, **kw) -> list:
+    """`FrameHeader` records (flac.common, reference common.py:263-271) of the frames scan_frames() finds,
+    parsed on the host from the few header bytes of each (decoder.py:133-185, :188-262)."""
+    from flac import coded_number
+    from flac.common import BlockingStrategy, CHANNELS_DECODING, FrameHeader, SAMPLE_RATE_VALUE_DECODING, SAMPLE_SIZE_DECODING
+    offs, sizes, _, _ = scan_frames(frames, sample_size, **kw)
+    raw = bytes(frames) if not isinstance(frames, (bytes, bytearray)) else frames
+    out = []
+    for k in range(len(offs) - 1):
+        h = raw[int(offs[k]):int(offs[k]) + 16]
+        rate_code, ss_code = h[2] & 15, (h[3] >> 1) & 7
+        nbytes = coded_number.following_bytes(h[4]) + 1
+        number = coded_number.decode(h[4:4 + nbytes])
+        p = 4 + nbytes + {6: 1, 7: 2}.get(h[2] >> 4, 0)
+        rate = None
+        if rate_code in SAMPLE_RATE_VALUE_DECODING:
+            rate = SAMPLE_RATE_VALUE_DECODING[rate_code].value
+        elif rate_code in (12, 13, 14):
+            w = 1 if rate_code == 12 else 2
+            rate = int.from_bytes(h[p:p + w], "big") * (1000 if rate_code == 12 else 10 if rate_code == 14 else 1)
+            p += w
+        out.append(FrameHeader(BlockingStrategy(h[1] & 1), int(sizes[k]), rate, CHANNELS_DECODING[h[3] >> 4],
+                               SAMPLE_SIZE_DECODING[ss_code].value if ss_code in SAMPLE_SIZE_DECODING else None, number, h[p]))
+    return out
+
+
 def decode_frames(frames, sample_size: int, *, devices: Optional[Sequence[int]] = None,
                   cap_sample_frames: Optional[int] = None) -> tuple[np.ndarray, int]:
     """-> (int32 array (n, frame_channels), frame_channels); raises what the reference raises."""

@@ -194,6 +194,29 @@ def encode_frames(sample_size: int, channels: int, pcm, parameters: EncoderParam
     return shards
 
 
+def subframe_records(shard: _Shard, precision: int) -> list:
+    """What the kernels decided, as the reference's records (flac.common, reference common.py:306-420):
+    one (SubframeHeader, Residual-shaped summary) pair per subframe of a shard encoded with want_info=True.
+    The records carry the decisions (type, order, shift, coefficients, coding method, Rice parameters), not
+    the samples: warm-up and residual lists hold `None` placeholders of the right length."""
+    from flac.common import (Residual, RiceCodingMethod, RicePartition, SubframeFixed, SubframeHeader, SubframeLPC,
+                             SubframeTypeFixed, SubframeTypeLPC)
+    out = []
+    for inf in shard.info or []:
+        lpc = bool(inf.type)
+        header = SubframeHeader(SubframeTypeLPC(inf.order) if lpc else SubframeTypeFixed(inf.order), 0)
+        warm = [None] * inf.order
+        if lpc:
+            m = inf.order - 1
+            body = SubframeLPC(warm, precision, inf.shift, list(inf.lpc_q[m][:inf.lpc_ncoef[m]]), [])
+        else:
+            body = SubframeFixed(warm, [])
+        parts = [RicePartition(int(k), []) for k in inf.params[:min(inf.nparams, len(inf.params))]]
+        parts += [RicePartition(-1, [])] * (inf.nparams - len(parts))  # beyond what the record holds
+        out.append((header, body, Residual(RiceCodingMethod(inf.method), parts)))
+    return out
+
+
 def _yield_shards(shards: list[_Shard]) -> Iterator[bytes]:
     """One chunk per frame in stream order; raises where the reference raises, after the frames
     before the failing one have been yielded (the reference's generator behaves the same)."""

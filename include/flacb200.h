@@ -180,6 +180,20 @@ int flacb_decode_frames(flacb_ctx *ctx, const uint8_t *frames, uint64_t len, int
 int flacb_decode_output(flacb_ctx *ctx, uint32_t flags, int32_t *pcm_out, uint64_t cap_samples,
                         uint64_t *n_sample_frames, int *frame_channels, flacb_stats *stats);
 
+/*
+ * The frame index of a stream: byte offsets (relative to `frames`) of the frames the reference's
+ * get_frames loop (decoder.py:100-108) visits, in stream order, and offsets[n] = the end of the
+ * last one; optionally their block sizes.  The reference can only find frame k by parsing frames
+ * 0 .. k-1 (frame lengths are not stored, STREAMINFO's frame sizes are zero, encoder.py:75-76);
+ * here every sync candidate is parsed in parallel and the real frames are the chain that starts
+ * at offset 0 -- the first half of flacb_decode_frames as a stage of its own, for seeking,
+ * SEEKTABLE writing (flac.encoder.seektable_block) and sharding a decode.  FLACB_E_NOSPACE:
+ * *n_frames frames exist, more than cap_frames.  The status is the one the decode would return.
+ */
+int flacb_scan_frames(flacb_ctx *ctx, const uint8_t *frames, uint64_t len, int streaminfo_bits,
+                      uint32_t flags, uint64_t *offsets, uint32_t *block_sizes, uint64_t cap_frames,
+                      uint64_t *n_frames, uint64_t *n_sample_frames, int *frame_channels);
+
 /* CUDA-event timer on the context's stream, for the benchmark (kernel-only throughput). */
 int flacb_timer_begin(flacb_ctx *ctx);
 int flacb_timer_end(flacb_ctx *ctx, float *ms);

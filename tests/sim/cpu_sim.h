@@ -163,9 +163,30 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
         f.ctx.uc_link = &s.main_ctx;
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
+    /* FLACB_SIM_ORDER: the order in which the threads of a CTA are resumed between their
+     * rendezvous points -- "reverse", or "random[:seed]" (a new permutation every sweep).  A kernel
+     * whose result depends on that order has a race between two barriers: the tests run the
+     * golden cases under several orders and compare bytes (the pool has no compute-sanitizer). */
+    std::vector<int> order((size_t)nthreads);
+    for (int t = 0; t < nthreads; t++) order[(size_t)t] = t;
+    const char *ord = getenv("FLACB_SIM_ORDER");
+    const bool rev = ord && !strncmp(ord, "reverse", 7), rnd = ord && !strncmp(ord, "random", 6);
+    unsigned long long rs = 0x9E3779B97F4A7C15ull ^ (unsigned long long)block;
+    if (rnd && ord[6] == ':') rs ^= strtoull(ord + 7, nullptr, 0) * 0xD1B54A32D192ED03ull;
+    if (rev)
+        for (int t = 0; t < nthreads; t++) order[(size_t)t] = nthreads - 1 - t;
     int alive = nthreads;
     while (alive > 0) {
-        for (int t = 0; t < nthreads; t++) {
+        if (rnd) {
+            for (int t = nthreads - 1; t > 0; t--) { /* Fisher-Yates with a xorshift generator */
+                rs ^= rs << 13, rs ^= rs >> 7, rs ^= rs << 17;
+                const int j = (int)(rs % (unsigned long long)(t + 1));
+                const int tmp = order[(size_t)t];
+                order[(size_t)t] = order[(size_t)j], order[(size_t)j] = tmp;
+            }
+        }
+        for (int k = 0; k < nthreads; k++) {
+            const int t = order[(size_t)k];
             Fiber &f = s.fibers[(size_t)t];
             if (f.done) continue;
             s.cur = t;

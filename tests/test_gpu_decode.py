@@ -152,3 +152,41 @@ def test_crafted_streams_decode_like_the_reference(name):
         raised = type(e).__name__
     assert raised == case["raises"]
     assert got == case["samples"]
+
+
+def test_scan_frames_gives_the_frame_index_and_headers():
+    """flacb_scan_frames / flac.decoder.scan_frames: the offsets of the frames of a golden stream are the
+    chunk boundaries the reference's encoder yielded; frame_headers() parses them into flac.common.FrameHeader"""
+    from flac.common import BlockingStrategy, Channels
+    from flac.decoder import frame_headers, scan_frames
+    for name in ("many_frames", "c2_white", "c3_white", "bs255"):
+        case = CASES[name]
+        s = case_stream(case)[42:]
+        offs, sizes, ns, rc = scan_frames(s, case["bits"])
+        assert rc == 0 and ns == case["n"]
+        want = np.cumsum([0] + case["chunk_lengths"][3:])
+        assert (offs == want).all()
+        assert sizes.sum() == case["n"] and (sizes[:-1] == case["block_size"]).all()
+        hs = frame_headers(s, case["bits"])
+        assert [h.coded_number for h in hs] == list(range(len(sizes)))
+        assert all(h.blocking_strategy is BlockingStrategy.Fixed and h.channels is Channels.L_R and h.sample_rate is None
+                   and h.sample_size is None for h in hs)
+        assert [h.block_size for h in hs] == [int(v) for v in sizes]
+
+
+def test_decode_sizes_its_output_from_the_stream_not_from_streaminfo():
+    """a STREAMINFO sample count of 2^36 - 1 (or 1) must not drive the allocation: the library says
+    how much the stream decodes to and hands the decoded frames over without decoding twice"""
+    import io
+    from flac.decoder import decode_frames, decode_pcm
+    case = CASES["c2_white"]
+    s = bytearray(case_stream(case))
+    x = case_pcm(case)
+    for total in ((1 << 36) - 1, 1):
+        v = int.from_bytes(s[18:26], "big")
+        v = (v & ~((1 << 36) - 1)) | total
+        s[18:26] = v.to_bytes(8, "big")
+        info, pcm = decode_pcm(io.BytesIO(bytes(s)))
+        assert info.samples == total and (pcm == x).all()
+    pcm, fch = decode_frames(bytes(s[42:]), 16, cap_sample_frames=3)  # far too small a hint
+    assert fch == 2 and (pcm == x).all()

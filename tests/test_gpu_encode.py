@@ -219,3 +219,21 @@ def test_sharding_over_two_gpus_in_one_process():
     x = case_pcm(case)
     stream = b"".join(encode_pcm(case["rate"], case["bits"], 2, S.pack_le(x, 16), _params(case), devices=[0, 1]))
     assert stream == case_stream(case)
+
+
+def test_subframe_records_use_the_reference_data_model():
+    from flac.common import RiceCodingMethod, SubframeFixed, SubframeLPC, SubframeTypeFixed, SubframeTypeLPC
+    from flac.encoder import subframe_records
+    case = CASES["c2_white"]
+    sh, _ = _encode(case_pcm(case), case["bits"], _params(case), want_info=True)
+    recs = subframe_records(sh, case["qlp_precision"])
+    assert len(recs) == len(case["subframes"])
+    for (header, body, residual), ref in zip(recs, case["subframes"]):
+        if ref["type"] == "lpc":
+            assert isinstance(header.type_, SubframeTypeLPC) and isinstance(body, SubframeLPC)
+            assert body.coefficients == ref["quant"][ref["order"] - 1][0] and body.shift == ref["quant"][ref["order"] - 1][1]
+        else:
+            assert isinstance(header.type_, SubframeTypeFixed) and isinstance(body, SubframeFixed)
+        assert header.type_.order == body.order == ref["order"]
+        assert residual.partition_order == ref["porder"] and residual.coding_method is RiceCodingMethod(ref["method"])
+        assert [p.parameter for p in residual.partitions][:64] == ref["params"][:64]

@@ -189,3 +189,27 @@ def test_chunk_plan_of_the_host_path():
                 for want, edge in ((0, 0), (5, 0), (16, 0), (100000, 0), (888, 7)):
                     q = simlib.chunk_plan(n, wave, pcm, want, edge)
                     assert q[0] == 0 and q[-1] == n and all(b > a for a, b in zip(q[:-1], q[1:])), (n, wave, pcm, want, edge, q[:6])
+
+
+def test_data_model_records_match_the_reference_names_and_tables():
+    """flac.common carries every record, enum and code table of the reference's data model (common.py:26-420)"""
+    import flac.common as c
+    for name in ("FrameHeader", "SubframeHeader", "SubframeTypeConstant", "SubframeTypeVerbatim", "SubframeTypeFixed",
+                 "SubframeTypeLPC", "SubframeConstant", "SubframeVerbatim", "SubframeFixed", "SubframeLPC", "Frame",
+                 "RicePartition", "EscapedPartition", "Residual", "RiceCodingMethod", "BlockSizeValue", "BlockSizeUncommon8",
+                 "BlockSizeUncommon16", "SampleRateValue", "SampleRateFromStreaminfo", "SampleSizeValue",
+                 "SAMPLE_RATE_VALUE_ENCODING", "SAMPLE_RATE_VALUE_DECODING", "SAMPLE_SIZE_ENCODING", "SAMPLE_SIZE_DECODING"):
+        assert hasattr(c, name), name
+    assert c.RiceCodingMethod.Rice4Bit.value == 4 and c.RiceCodingMethod.Rice5Bit.value == 5
+    assert c.SAMPLE_RATE_VALUE_ENCODING[c.SampleRateValue.V_44_1_kHz] == 0b1001 and c.SampleRateValue.V_22_05_kHz.value == 22050
+    assert c.SAMPLE_RATE_VALUE_DECODING[0b1100] is c.SampleRateValue.V_96_kHz
+    assert c.SAMPLE_SIZE_ENCODING[c.SampleSizeValue.V_24] == 0b110 and 0b011 not in c.SAMPLE_SIZE_DECODING
+    assert c.Channels.S_R.decorrelation_bit == [1, 0] and c.Channels.M_S.decorrelation_bit == [0, 1]
+    assert c.Channels.FL_FR_FC_LFE_BL_BR.decorrelation_bit == [0] * 6
+    lpc = c.SubframeLPC([1, 2, 3], 5, 7, [1, -2, 3], [0] * 10)
+    assert lpc.order == 3 and repr(lpc) == "SubframeLPC(order=3, precision=5, shift=7, coefficients=[1, -2, 3])"
+    assert repr(c.SubframeFixed([1], [2, 3])) == "SubframeFixed(order=1)"
+    r = c.Residual(c.RiceCodingMethod.Rice4Bit, [c.RicePartition(3, [1, 2])] * 8)
+    assert r.partition_order == 3 and repr(r.partitions[0]) == "RicePartition(parameter=3, samples_count=2)"
+    h = c.FrameHeader(c.BlockingStrategy.Fixed, 4608, None, c.Channels.L_R, None, 7)
+    assert h.crc is None and c.Frame(h, [], 0).header is h

@@ -250,3 +250,22 @@ def test_sim_serialise_kernel_partial_threads_and_rice_min():
     a = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6, flags=simlib.FLAG_LENIENT)
     b = simlib.encode_frames(x, 16, 2304, 8, 7, 1, 6, flags=simlib.FLAG_LENIENT, plane_mode=SER2, threads=192)
     assert a[0] == b[0] and a[1] == b[1]
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:1", "random:2"])
+@pytest.mark.parametrize("name", ["c2_white", "c1_sine", "bs255", "c4_mixed"])
+def test_sim_thread_order_does_not_change_the_stream(name, order, monkeypatch):
+    """Race check on the simulator (compute-sanitizer is closed on the GPU pool): the threads of a CTA are
+    resumed in reverse / in a new random order after every rendezvous.  A read that races with a write
+    between two barriers -- in-place residuals, atomic-or packing, scan scratch reuse -- would change bytes.
+    Both serialising kernels, the analysis / choice stages and the decoder."""
+    monkeypatch.setenv("FLACB_SIM_ORDER", order)
+    case = CASES[name]
+    x = case_pcm(case)
+    ref = case_stream(case)[42:]
+    for mode in (0, SER2, SER2 | 0x3000, SER2 | 0x4000):
+        rc, data, offs, _, _ = simlib.encode_frames(x, case["bits"], plane_mode=mode, **case_kwargs(case))
+        assert rc == 0 and data == ref, hex(mode)
+    rc, pcm, fch, _ = simlib.decode_frames(ref, case["bits"])
+    if case["channels"] == 2:
+        assert rc == 0 and (pcm == x).all()
