@@ -542,13 +542,21 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
     }
     /* how choose_kernel multiplies: sample pairs against coefficient bytes (16-bit PCM, at most
      * 8-bit coefficients), 32-bit sums proven exact for every order, or decided per order */
+    /* ... or, for samples wider than 16 bits with coefficients of at most 8 bits, as byte planes on the
+     * tensor cores (flavour 3, flacb200_choose_mma.cuh) */
     int flavour = 2;
     if (a.bits <= 16 && a.qlp_precision <= 8) flavour = 0;
+    else if (a.qlp_precision <= 8 && a.bits <= 24 && a.max_lpc_order > 16) flavour = 3; /* measured: below that the scalar filter is faster */
     else if (((u64)a.max_lpc_order << (a.qlp_precision - 1 + a.bits - 1)) <= (1ull << 30)) flavour = 1;
-    if (const char *e = getenv("FLACB200_FLAVOUR")) { /* tuning knob: a slower but equally exact flavour */
+    if (const char *e = getenv("FLACB200_FLAVOUR")) { /* tuning / test knob: another, equally exact flavour */
         const int v = atoi(e);
-        if (v > flavour && v <= 2) flavour = v;
+        if (v == 3 && a.qlp_precision <= 8 && a.bits <= 24) flavour = 3;
+        else if (v == 2 || (v == 1 && ((u64)a.max_lpc_order << (a.qlp_precision - 1 + a.bits - 1)) <= (1ull << 30)) ||
+                 (v == 0 && a.bits <= 16 && a.qlp_precision <= 8))
+            flavour = v;
     }
+    const MmaLayout mlay = make_layout_choose_mma(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, 256);
+    if (flavour == 3 && (size_t)mlay.total + 16384 > (size_t)c->smem_optin) flavour = 2; /* the planes of a block do not fit */
     /* stage events in between (FLACB_STAGE_TIMES) keep the stages apart; without them the stages behind the
      * first are launched with programmatic stream serialisation (FLACB200_NO_PDL=1: plain launches) */
     const bool stage_times = (a.flags & FLACB_STAGE_TIMES) != 0;
@@ -562,6 +570,19 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
                            : launch_32(kind, variant, fl, grid, threads, smem, sl.stream, kp);
     };
 
+    /* FLACB200_DEBUG_SYNC=1 (development aid): wait behind every stage, so that a fault names its kernel */
+    const bool dbg_sync = getenv("FLACB200_DEBUG_SYNC") != nullptr;
+    auto stage_done = [&](const char *what) -> int {
+        if (!dbg_sync) return FLACB_OK;
+        cudaError_t e = cudaStreamSynchronize(sl.stream);
+        if (e != cudaSuccess) {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "stage %s: %s", what, cudaGetErrorString(e));
+            g_cuda_error = buf;
+            return FLACB_E_CUDA;
+        }
+        return FLACB_OK;
+    };
     CUDA_TRY(cudaMemsetAsync(dmeta + o_misc, 0, o_lb + n_frames * 8 - o_misc, sl.stream)); /* counters, statuses, look-back words */
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
     sl.staged = !plan.staged ? 0 : stage_times ? 1 : 2;
@@ -571,6 +592,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
                                    plan.front.all_planes);
         pa.all_planes = plan.front.all_planes;
         CUDA_TRY(launch(K_ANALYSE, plan.front.variant, plan.front.threads, pa.lay.total, pa));
+        if ((rc = stage_done("A (analyse_kernel)"))) return rc;
         if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[0], sl.stream));
         const int wpb = 4; /* subframes (warps) per CTA of stage B */
         const size_t smem_b = (size_t)wpb * p.pre_stride;
@@ -595,12 +617,21 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
             CUDA_TRY(cudaGetLastError());
         }
         g_launches++;
+        if ((rc = stage_done("B (lpc_coefficients_kernel)"))) return rc;
         if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[1], sl.stream));
         EncParams pc = p;
         pc.lay = make_layout_choose(a.block_size, a.channels, a.bits, a.rice_max, a.max_lpc_order, plan.choose.threads,
                                     plan.choose.all_planes);
         pc.all_planes = plan.choose.all_planes;
-        CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
+        if (flavour == 3) {
+            EncParams pm = p;
+            pm.lay = lay_rec;
+            g_launches++;
+            CUDA_TRY(plan.lmax12 ? launch_mma_12(pdl, (unsigned)n_frames, 256, mlay.total, sl.stream, pm, mlay)
+                                 : launch_mma_32(pdl, (unsigned)n_frames, 256, mlay.total, sl.stream, pm, mlay));
+        } else
+            CUDA_TRY(launch(K_CHOOSE, plan.choose.variant, plan.choose.threads, pc.lay.total, pc));
+        if ((rc = stage_done(flavour == 3 ? "C1 (choose_mma_kernel)" : "C1 (choose_kernel)"))) return rc;
         if (stage_times) CUDA_TRY(cudaEventRecord(sl.ev_s[2], sl.stream));
     }
     if (plan.ser2) {
@@ -619,6 +650,7 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         CUDA_TRY(cudaGetLastError());
         g_launches += 2;
     }
+    if ((rc = stage_done("C2 (serialising kernel)"))) return rc;
     CUDA_TRY(cudaEventRecord(sl.ev_k1, sl.stream));
 
     uint8_t *h = (uint8_t *)sl.h_meta.p;

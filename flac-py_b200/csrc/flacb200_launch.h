@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "flacb200_kernels.cuh"
+#include "flacb200_choose_mma.cuh"
 
 namespace flacb {
 
@@ -47,5 +48,7 @@ FLACB_TU_DECL(fixed)
 FLACB_TU_DECL(12)
 FLACB_TU_DECL(32)
 #undef FLACB_TU_DECL
+cudaError_t launch_mma_12(bool pdl, unsigned grid, int threads, size_t smem, cudaStream_t stream, const EncParams &p, const MmaLayout &ml);
+cudaError_t launch_mma_32(bool pdl, unsigned grid, int threads, size_t smem, cudaStream_t stream, const EncParams &p, const MmaLayout &ml);
 
 } /* namespace flacb */

@@ -7,6 +7,7 @@
 #include <string.h>
 #include "flacb200_launch.h"
 #include "flacb200_serialise.cuh"
+#include "flacb200_choose_mma.cuh"
 
 namespace flacb {
 
@@ -44,6 +45,29 @@ static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem,
     kernel<<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
+
+#if FLACB_TU_LMAX
+/* stage C1 on the tensor cores (flacb200_choose_mma.cuh) */
+cudaError_t FLACB_CAT(launch_mma_, FLACB_TU_NAME)(bool pdl, unsigned grid, int threads, size_t smem, cudaStream_t stream,
+                                                   const EncParams &p, const MmaLayout &ml)
+{
+    auto kernel = choose_mma_kernel<FLACB_TU_LMAX, 256, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p, ml);
+}
+#endif
 
 cudaError_t FLACB_CAT(launch_, FLACB_TU_NAME)(int kind, int variant, int flavour, unsigned grid, int threads, size_t smem,
                                                cudaStream_t stream, const EncParams &p)

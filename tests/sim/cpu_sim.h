@@ -55,7 +55,7 @@ struct State {
     int wbar_count[64];
     unsigned wbar_gen[64];
     unsigned long long wbuf[64][32];
-    unsigned char *dyn_smem = nullptr;
+    unsigned char *dyn_smem = nullptr, *dyn_alloc = nullptr;
     std::function<void()> body;
 };
 
@@ -147,8 +147,13 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
     memset(s.nbar_count, 0, sizeof(s.nbar_count));
     memset(s.wbar_count, 0, sizeof(s.wbar_count));
     s.body = body;
-    s.dyn_smem = (unsigned char *)aligned_alloc(128, (dyn_smem_bytes + 127) / 128 * 128 + 128);
-    memset(s.dyn_smem, 0xA5, dyn_smem_bytes); /* shared memory is not zero initialised */
+    /* the dynamic shared memory ENDS where its allocation ends (and is 16-byte aligned like on the
+     * device), so that an address sanitizer build catches any access behind the launch's window */
+    const size_t smem_len = (dyn_smem_bytes + 15) / 16 * 16;
+    const size_t alloc_len = (smem_len + 127) / 128 * 128 + 128;
+    s.dyn_alloc = (unsigned char *)aligned_alloc(128, alloc_len);
+    s.dyn_smem = s.dyn_alloc + (alloc_len - smem_len);
+    memset(s.dyn_smem, 0xA5, smem_len); /* shared memory is not zero initialised */
     g_blockIdx = {block, 0, 0};
     g_gridDim = {grid, 1, 1};
     g_blockDim = {(unsigned)nthreads, 1, 1};
@@ -196,7 +201,7 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
         }
     }
     for (int t = 0; t < nthreads; t++) free(s.fibers[(size_t)t].stack);
-    free(s.dyn_smem);
+    free(s.dyn_alloc);
     s.dyn_smem = nullptr;
 }
 

@@ -17,6 +17,7 @@ sim_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 #include "../../flac-py_b200/csrc/flacb200_host.h"
 #include "../../flac-py_b200/csrc/flacb200_kernels.cuh"
 #include "../../flac-py_b200/csrc/flacb200_serialise.cuh"
+#include "../../flac-py_b200/csrc/flacb200_choose_mma.cuh"
 #include "../../flac-py_b200/csrc/flacb200_decode.cuh"
 
 using namespace flacb;
@@ -139,9 +140,26 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
         pc.all_planes = front_planes;
         int flavour = 2;
         if (bits <= 16 && qlp_precision <= 8) flavour = 0;
+        else if (qlp_precision <= 8 && bits <= 24 && max_lpc_order > 16) flavour = 3; /* the library's choice for wide samples and high orders: tensor cores */
         else if (((u64)max_lpc_order << (qlp_precision - 1 + bits - 1)) <= (1ull << 30)) flavour = 1;
-        if ((int)((plane_mode >> 9) & 3u) > flavour) flavour = (int)((plane_mode >> 9) & 3u);
-        for (uint64_t f = 0; f < n_frames; f++) {
+        {
+            /* plane_mode bits 9-10: another, equally exact flavour (1, 2: scalar; 3: tensor cores, also for 16 bits);
+             * bit 15: the scalar flavour the library would pick without the tensor-core path */
+            const int v = (int)((plane_mode >> 9) & 3u);
+            if (v == 3 && qlp_precision <= 8 && bits <= 24) flavour = 3;
+            else if (v == 2 || (v == 1 && ((u64)max_lpc_order << (qlp_precision - 1 + bits - 1)) <= (1ull << 30))) flavour = v;
+            if ((plane_mode & 0x8000u) && flavour == 3) flavour = ((u64)max_lpc_order << (qlp_precision - 1 + bits - 1)) <= (1ull << 30) ? 1 : 2;
+        }
+        const MmaLayout mlay = make_layout_choose_mma(block_size, channels, bits, rice_max, max_lpc_order, 256);
+        for (uint64_t f = 0; f < n_frames && flavour == 3; f++) {
+            EncParams pm = p;
+            pm.lay = lay_rec;
+            if (max_lpc_order <= 12)
+                sim::run_block((unsigned)f, (unsigned)n_frames, 256, mlay.total, [&]() { choose_mma_kernel<12, 256, 2>(pm, mlay); });
+            else
+                sim::run_block((unsigned)f, (unsigned)n_frames, 256, mlay.total, [&]() { choose_mma_kernel<32, 256, 2>(pm, mlay); });
+        }
+        for (uint64_t f = 0; f < n_frames && flavour != 3; f++) {
             const unsigned fu = (unsigned)f, g = (unsigned)n_frames;
             if (max_lpc_order <= 12) {
                 if (flavour == 0) sim::run_block(fu, g, B, pc.lay.total, [&]() { choose_kernel<12, 576, 1, 0, 0>(pc); });

@@ -237,3 +237,18 @@ def test_subframe_records_use_the_reference_data_model():
         assert header.type_.order == body.order == ref["order"]
         assert residual.partition_order == ref["porder"] and residual.coding_method is RiceCodingMethod(ref["method"])
         assert [p.parameter for p in residual.partitions][:64] == ref["params"][:64]
+
+
+@pytest.mark.parametrize("flavour", ["3", "2", "1"])
+@pytest.mark.parametrize("name", ["c3_white", "c3_clip", "c4_mixed", "c4_white", "c2_white", "q8_white", "bs255", "many_frames"])
+def test_golden_stream_bytes_every_filter_flavour(name, flavour, monkeypatch):
+    """stage C1, the all-orders LPC filter: FLACB200_FLAVOUR=3 byte planes on the tensor cores (mma.sync s8; the
+    default for samples wider than 16 bits, forced here for 16-bit samples too), 2 / 1 the scalar flavours"""
+    monkeypatch.setenv("FLACB200_FLAVOUR", flavour)
+    case = CASES[name]
+    sh, _ = _encode(case_pcm(case), case["bits"], _params(case), want_info=True)
+    assert sh.rc == 0
+    assert sh.out.tobytes() == case_stream(case)[42:]
+    for info, ref in zip(sh.info, case["subframes"]):
+        if case["max_lpc_order"] > 0 and ref.get("lpc_total") is not None:
+            assert info.lpc_order == ref["lpc_order"] and info.lpc_err[info.lpc_order - 1] == ref["lpc_total"]

@@ -269,3 +269,18 @@ def test_sim_thread_order_does_not_change_the_stream(name, order, monkeypatch):
     rc, pcm, fch, _ = simlib.decode_frames(ref, case["bits"])
     if case["channels"] == 2:
         assert rc == 0 and (pcm == x).all()
+
+
+@pytest.mark.parametrize("name", ["c3_white", "c4_mixed", "c2_white", "q8_white", "bs255", "bs192_r0"])
+def test_sim_tensor_core_filter_matches_golden_and_the_scalar_flavours(name):
+    """choose_mma_kernel (plane_mode bits 9-10 = 3): sample byte planes x coefficient bytes through an emulated
+    mma.m16n8k32 -- same sums of |residual| for every order as the scalar flavours (bit 15), same bytes as the goldens;
+    three planes for 24-bit samples, two for 16-bit, tails shorter than a tile, orders 12 and 32"""
+    case = CASES[name]
+    x = case_pcm(case)
+    a = simlib.encode_frames(x, case["bits"], plane_mode=3 << 9, want_info=True, **case_kwargs(case))
+    b = simlib.encode_frames(x, case["bits"], plane_mode=0x8000 | (2 << 9), want_info=True, **case_kwargs(case))
+    assert a[0] == 0 and a[1] == case_stream(case)[42:] == b[1]
+    L = case["max_lpc_order"]
+    for ia, ib in zip(a[3], b[3]):
+        assert [ia.lpc_err[m] for m in range(L)] == [ib.lpc_err[m] for m in range(L)]
