@@ -33,6 +33,8 @@ constexpr int MMA_PADB = 48; /* bytes behind it */
 struct MmaLayout {
     uint32_t bpl, bstride; /* byte planes of one channel: plane p at bpl + p * bstride */
     uint32_t red, qb, lpc, lpc_stride, total; /* qb: the current channel's coefficient bytes, [32 orders][32 taps] */
+    /* what the kernel keeps of a subframe's record (no Levinson matrix): offsets inside its lpc_stride bytes */
+    uint32_t c_autoc, c_qc, c_qmeta, c_fixed;
     int planes;
 };
 
@@ -47,7 +49,11 @@ __host__ __device__ inline MmaLayout make_layout_choose_mma(int nmax, int channe
     const uint32_t thr = (uint32_t)((threads + 31) / 32 * 32);
     l.red = off; off += align16((thr / 32) * 32u * 8u);
     l.qb = off; off += 32u * 32u;
-    l.lpc_stride = rec.lpc_stride;
+    l.c_autoc = 0;
+    l.c_qc = rec.o_levprod - rec.o_autoc;
+    l.c_qmeta = l.c_qc + (rec.o_qmeta - rec.o_qc);
+    l.c_fixed = l.c_qmeta + (rec.o_fixed - rec.o_qmeta);
+    l.lpc_stride = align16(l.c_fixed + 64);
     l.lpc = off; off += l.lpc_stride * (uint32_t)channels;
     l.total = off;
     return l;
@@ -119,10 +125,15 @@ __device__ void lpc_errors_mma(Blk &b, const uint8_t *bpl, uint32_t bstride, int
     const int g = b.lane >> 2, t = b.lane & 3;
     const int NT = (L + 7) >> 3; /* column tiles of 8 orders */
     const bool short_taps = L <= 16; /* taps 16..31 (k < 16) meet zero coefficients only */
-    /* 32-bit reassembly of the planes is exact when the prediction sums fit 31 bits for every order */
-    uint32_t qabs_max = 0;
-    for (int m = 0; m < L; m++) qabs_max = b.qabs[m] > qabs_max ? b.qabs[m] : qabs_max;
-    const bool narrow = ((u64)qabs_max << (b.p.bps - 1)) < (1ull << 30);
+    /* The planes reassemble to a prediction sum of up to 8 NP + 13 bits.  Once shifted it fits 32 bits whenever
+     * sum |q| * 2^(bps-1) >> shift stays below 2^30 (every sane filter): the residual is then 32-bit work on the
+     * low word of a 64-bit funnel shift.  Anything else takes the full 64-bit path (block-uniform choice). */
+    bool fits = true;
+    for (int m = 0; m < L; m++)
+        if (b.qncoef[m] != 0 && (((u64)b.qabs[m] << (b.p.bps - 1)) >> b.qshift[m]) >= (1ull << 30)) fits = false;
+#ifdef FLACB_CPU_SIM
+    if (getenv("FLACB_SIM_MMA_WIDE")) fits = false; /* the tests walk the 64-bit path too */
+#endif
     /* the thread's order columns: tile nt -> orders nt * 8 + 2 t + {1, 2} */
     u64 acc[4][2];
 #pragma unroll
@@ -178,29 +189,35 @@ __device__ void lpc_errors_mma(Blk &b, const uint8_t *bpl, uint32_t bstride, int
                     else mma_bytes<false>(c[p], a[p], bf);
                 }
                 /* epilogue: prediction sum -> residual -> |residual| (encoder.py:544-548, :398) */
+                if (fits && interior) { /* warp-uniform: nothing to mask, 32-bit residuals */
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    uint32_t t32 = 0;
-                    u64 t64 = 0;
+                    for (int j = 0; j < 2; j++) {
+                        uint32_t t32 = 0;
 #pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int i = s0 + g + 8 * r, m = nt * 8 + 2 * t + j + 1;
-                        const bool ok = live[nt][j] && (interior || (i >= m && i < n));
-                        if (narrow) {
-                            int pred = c[NP - 1][2 * r + j];
+                        for (int r = 0; r < 2; r++) {
+                            int hi = c[NP - 1][2 * r + j]; /* planes 1.. as one 32-bit sum (< 2^28) */
 #pragma unroll
-                            for (int p = NP - 2; p >= 0; p--) pred = (pred << 8) + c[p][2 * r + j];
-                            const int rr = xr[r] - (pred >> shift[nt][j]);
-                            if (ok) t32 += (uint32_t)abs(rr);
-                        } else {
+                            for (int p = NP - 2; p >= 1; p--) hi = (hi << 8) + c[p][2 * r + j];
+                            const i64 pred = NP > 1 ? (i64)hi * 256 + (i64)c[0][2 * r + j] : (i64)hi;
+                            t32 += (uint32_t)abs(xr[r] - (int)(uint32_t)(u64)(pred >> shift[nt][j]));
+                        }
+                        acc[nt][j] += (u64)t32;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        u64 t64 = 0;
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            const int i = s0 + g + 8 * r, m = nt * 8 + 2 * t + j + 1;
                             i64 pred = c[NP - 1][2 * r + j];
 #pragma unroll
                             for (int p = NP - 2; p >= 0; p--) pred = pred * 256 + (i64)c[p][2 * r + j];
                             const i64 rr = (i64)xr[r] - (pred >> shift[nt][j]);
-                            if (ok) t64 += (u64)(rr < 0 ? -rr : rr);
+                            if (i >= m && i < n) t64 += (u64)(rr < 0 ? -rr : rr);
                         }
+                        acc[nt][j] += t64;
                     }
-                    acc[nt][j] += narrow ? (u64)t32 : t64;
                 }
             }
         }
@@ -214,7 +231,7 @@ __device__ void lpc_errors_mma(Blk &b, const uint8_t *bpl, uint32_t bstride, int
             v += __shfl_xor_sync(FULL, v, 4);
             v += __shfl_xor_sync(FULL, v, 8);
             v += __shfl_xor_sync(FULL, v, 16);
-            if (g == 0) red[b.warp * 32 + nt * 8 + 2 * t + j] = v;
+            if (g == 0) red[b.warp * 32 + nt * 8 + 2 * t + j] = live[nt][j] ? v : 0;
         }
     }
     __syncthreads();
@@ -269,13 +286,16 @@ __global__ void __launch_bounds__(TB, MINB) choose_mma_kernel(const EncParams p,
     for (int c = 0; c < p.channels; c++) {
         const uint32_t *rec = (const uint32_t *)(p.pre + ((u64)f * (u64)p.channels + (u64)c) * (u64)p.pre_stride);
         uint32_t *loc = (uint32_t *)(smem + ml.lpc + (uint32_t)c * ml.lpc_stride);
-        for (uint32_t i = (uint32_t)b.tid; i < lay.o_levprod / 4; i += (uint32_t)b.B) loc[i] = rec[i];
-        for (uint32_t i = lay.o_qc / 4 + (uint32_t)b.tid; i < ml.lpc_stride / 4; i += (uint32_t)b.B) loc[i] = rec[i];
+        /* autocorrelation (for the introspection record), then everything behind the Levinson matrix */
+        for (uint32_t i = (uint32_t)b.tid; i < (lay.o_levprod - lay.o_autoc) / 4; i += (uint32_t)b.B) loc[i] = rec[lay.o_autoc / 4 + i];
+        for (uint32_t i = (uint32_t)b.tid; i < (lay.o_fixed + 64 - lay.o_qc) / 4; i += (uint32_t)b.B) loc[ml.c_qc / 4 + i] = rec[lay.o_qc / 4 + i];
     }
+    SmemLayout clay = lay; /* the same record, compacted */
+    clay.o_autoc = ml.c_autoc, clay.o_levprod = ml.c_autoc, clay.o_ldc = ml.c_autoc, clay.o_qc = ml.c_qc, clay.o_qmeta = ml.c_qmeta, clay.o_fixed = ml.c_fixed;
     __syncthreads();
     for (int c = 0; c < p.channels; c++) {
         unsigned char *q = smem + ml.lpc + (uint32_t)c * ml.lpc_stride;
-        bind_lpc_record(b, q, lay, p.L);
+        bind_lpc_record(b, q, clay, p.L);
         if (b.tid == 0) sh.cur_ch = c;
         /* coefficient bytes, taps reversed, zero beyond the order (and for orders without coefficients):
          * qb[m1][31 - j] = q_{m1 + 1}[j] */

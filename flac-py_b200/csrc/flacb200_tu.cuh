@@ -51,7 +51,7 @@ static cudaError_t launch_one(K kernel, unsigned grid, int threads, size_t smem,
 cudaError_t FLACB_CAT(launch_mma_, FLACB_TU_NAME)(bool pdl, unsigned grid, int threads, size_t smem, cudaStream_t stream,
                                                    const EncParams &p, const MmaLayout &ml)
 {
-    auto kernel = choose_mma_kernel<FLACB_TU_LMAX, 256, 2>;
+    auto kernel = choose_mma_kernel<FLACB_TU_LMAX, 256, 3>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;

@@ -284,3 +284,14 @@ def test_sim_tensor_core_filter_matches_golden_and_the_scalar_flavours(name):
     L = case["max_lpc_order"]
     for ia, ib in zip(a[3], b[3]):
         assert [ia.lpc_err[m] for m in range(L)] == [ib.lpc_err[m] for m in range(L)]
+
+
+@pytest.mark.parametrize("name", ["c3_white", "bs255"])
+def test_sim_tensor_core_filter_64_bit_path(name, monkeypatch):
+    """the epilogue that keeps 64-bit residuals (prediction sums that do not fit 32 bits once shifted: no filter a
+    sane signal produces) is forced on: same bytes"""
+    case = CASES[name]
+    x = case_pcm(case)
+    monkeypatch.setenv("FLACB_SIM_MMA_WIDE", "1")
+    a = simlib.encode_frames(x, case["bits"], plane_mode=3 << 9, **case_kwargs(case))
+    assert a[0] == 0 and a[1] == case_stream(case)[42:]
