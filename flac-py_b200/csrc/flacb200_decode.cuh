@@ -703,43 +703,63 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) decode_frames_kernel(const 
 /* result[i] += (sum_j result[i-1-j] * c[j]) >> shift, serially: one thread per subframe, the last
  * W samples and the coefficients in registers (W >= order, coefficients beyond the order are
  * zero).  The term of the newest sample is added last, so the chain from one sample to the next
- * is one multiply-add, a shift and an add.  Residuals are read eight at a time, one chunk ahead
- * of the arithmetic (the plane is rewritten in place, and a load behind a store to the same
- * line would wait for L2 on every sample). */
+ * is short.  Residuals are read eight at a time, several chunks ahead of the arithmetic (the plane is
+ * rewritten in place). */
 constexpr int RESTORE_CHUNK = 8;
+#ifndef FLACB_RESTORE_AHEAD
+#define FLACB_RESTORE_AHEAD 4
+#endif
 
 template <int W>
-__device__ __forceinline__ void restore_run(int32_t *x, int bs, int order, int shift, const int (&c)[W])
+__device__ __forceinline__ void restore_run(int32_t *x, int bs, int order, int shift, const int (&ci)[W])
 {
-    int h[W]; /* h[j] = x[i - 1 - j] */
+    /* The sum of up to 32 products of a 32-bit sample and a 15-bit coefficient is an integer below 2^51: fp64
+     * multiply-adds carry it exactly, one instruction per tap (the 64-bit integer form costs three), and the chain
+     * from one sample to the next is convert, multiply-add, scale, floor-convert, add. */
+    double c[W], h[W]; /* h[j] = x[i - 1 - j] */
 #pragma unroll
-    for (int j = 0; j < W; j++) h[j] = j < order ? x[order - 1 - j] : 0;
-    int cur[RESTORE_CHUNK], nxt[RESTORE_CHUNK];
+    for (int j = 0; j < W; j++) c[j] = (double)ci[j], h[j] = j < order ? (double)x[order - 1 - j] : 0.0;
+    const double scale = __longlong_as_double((long long)(1023 - shift) << 52); /* 2^-shift */
+    /* residuals are fetched RESTORE_AHEAD chunks (about 1500 cycles of arithmetic) before their turn: the planes
+     * come from DRAM, every lane from a line of its own, and the chunk behind a store would otherwise wait there */
+    constexpr int RESTORE_AHEAD = W > 16 ? 2 : FLACB_RESTORE_AHEAD; /* the 32-tap instance has no registers to spare */
+    int q[RESTORE_AHEAD][RESTORE_CHUNK];
 #pragma unroll
-    for (int e = 0; e < RESTORE_CHUNK; e++) cur[e] = order + e < bs ? x[order + e] : 0;
-    for (int i0 = order; i0 < bs; i0 += RESTORE_CHUNK) {
+    for (int k = 0; k < RESTORE_AHEAD; k++)
 #pragma unroll
-        for (int e = 0; e < RESTORE_CHUNK; e++) nxt[e] = i0 + RESTORE_CHUNK + e < bs ? x[i0 + RESTORE_CHUNK + e] : 0;
+        for (int e = 0; e < RESTORE_CHUNK; e++) q[k][e] = order + k * RESTORE_CHUNK + e < bs ? x[order + k * RESTORE_CHUNK + e] : 0;
+    for (int i0 = order; i0 < bs; i0 += RESTORE_CHUNK * RESTORE_AHEAD) {
 #pragma unroll
-        for (int e = 0; e < RESTORE_CHUNK; e++) {
-            i64 a0 = 0, a1 = 0;
+        for (int k = 0; k < RESTORE_AHEAD; k++) {
+            const int ik = i0 + k * RESTORE_CHUNK;
+            if (ik >= bs) break;
+            int cur[RESTORE_CHUNK];
 #pragma unroll
-            for (int j = W - 1; j >= 1; j--) {
-                if (j & 1) a1 += (i64)h[j] * (i64)c[j];
-                else a0 += (i64)h[j] * (i64)c[j];
+            for (int e = 0; e < RESTORE_CHUNK; e++) cur[e] = q[k][e];
+#pragma unroll
+            for (int e = 0; e < RESTORE_CHUNK; e++) {
+                const int in = ik + RESTORE_CHUNK * RESTORE_AHEAD + e;
+                q[k][e] = in < bs ? x[in] : 0;
             }
-            const i64 acc = (a0 + a1) + (i64)h[0] * (i64)c[0];
-            const int32_t v = (int32_t)((i64)cur[e] + (acc >> shift));
 #pragma unroll
-            for (int j = W - 1; j > 0; j--) h[j] = h[j - 1];
-            h[0] = v;
-            cur[e] = v;
+            for (int e = 0; e < RESTORE_CHUNK; e++) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int j = W - 1; j >= 1; j--) {
+                    if (j & 1) a1 = __fma_rn(h[j], c[j], a1);
+                    else a0 = __fma_rn(h[j], c[j], a0);
+                }
+                const double acc = __fma_rn(h[0], c[0], __dadd_rn(a0, a1));
+                const int32_t v = (int32_t)((i64)cur[e] + __double2ll_rd(__dmul_rn(acc, scale)));
+#pragma unroll
+                for (int j = W - 1; j > 0; j--) h[j] = h[j - 1];
+                h[0] = (double)v;
+                cur[e] = v;
+            }
+#pragma unroll
+            for (int e = 0; e < RESTORE_CHUNK; e++)
+                if (ik + e < bs) x[ik + e] = cur[e];
         }
-#pragma unroll
-        for (int e = 0; e < RESTORE_CHUNK; e++)
-            if (i0 + e < bs) x[i0 + e] = cur[e];
-#pragma unroll
-        for (int e = 0; e < RESTORE_CHUNK; e++) cur[e] = nxt[e];
     }
 }
 
@@ -768,13 +788,23 @@ __device__ __forceinline__ void restore_any(int32_t *x, const SubRec &r)
 __global__ void __launch_bounds__(64) restore_kernel(const SubRec *recs, uint32_t n_cand, int32_t *tmp)
 {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (u64)n_cand * SUBREC_SLOTS) return;
+    const bool in_range = t < (u64)n_cand * SUBREC_SLOTS;
     const uint32_t ch = (uint32_t)(t / n_cand), ci = (uint32_t)(t - (u64)ch * n_cand);
-    const SubRec &r = recs[(u64)ci * SUBREC_SLOTS + ch];
-    if (r.kind == 0) return;
+    const SubRec &r = recs[in_range ? (u64)ci * SUBREC_SLOTS + ch : 0];
+    const bool work = in_range && r.kind != 0;
+    /* one filter length for the whole warp (the longest order among its subframes, the others' taps zero):
+     * lanes that took different lengths ran one after the other, each with the full cost of moving the samples */
+#ifdef FLACB_RESTORE_DIVERGENT
+    const int wmax = work ? r.order : 0;
+#else
+    const int wmax = (int)__reduce_max_sync(0xffffffffu, work ? (unsigned)r.order : 0u);
+#endif
+    if (!work) return;
     int32_t *x = tmp + r.off;
-    if (r.order <= 8) restore_any<8>(x, r);
-    else if (r.order <= 16) restore_any<16>(x, r);
+    if (wmax <= 4) restore_any<4>(x, r); /* every fixed predictor */
+    else if (wmax <= 8) restore_any<8>(x, r);
+    else if (wmax <= 12) restore_any<12>(x, r);
+    else if (wmax <= 16) restore_any<16>(x, r);
     else restore_any<32>(x, r);
 }
 

@@ -264,6 +264,18 @@ template <class T> static inline T __reduce_min_sync(unsigned, T v)
     sim::syncwarp();
     return r;
 }
+template <class T> static inline T __reduce_max_sync(unsigned, T v)
+{
+    sim::State &s = sim::st();
+    const int w = s.cur >> 5, lane = s.cur & 31;
+    s.wbuf[w][lane] = (unsigned long long)v;
+    sim::syncwarp();
+    T r = v;
+    for (int l = 0; l < 32; l++)
+        if ((T)s.wbuf[w][l] > r) r = (T)s.wbuf[w][l];
+    sim::syncwarp();
+    return r;
+}
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
 {
     const unsigned long long v = ((unsigned long long)b << 32) | a;
@@ -285,6 +297,9 @@ static inline double __dmul_rn(double a, double b) { volatile double r = a * b; 
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline long long __double2ll_rd(double a) { return (long long)floor(a); }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }

