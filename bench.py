@@ -150,11 +150,11 @@ def bind_near_gpu(local_rank: int) -> str:
     return "not bound"
 
 
-def ncu_traffic(workload: str):
+def ncu_traffic(workload: str, kernel: str):
     """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (or None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return int(json.load(f)[workload]["bytes"])
+            return int(json.load(f)[workload][kernel]["bytes"])
     except Exception:  # noqa: BLE001
         return None
 
@@ -702,7 +702,7 @@ def main():
         peak, peak_src = peak_hbm()
         k_ms = float(np.mean(kernel_ms))
         stages = [float(v) for v in np.mean(np.array(stage_ms), axis=0)]
-        stage_names = ["analyse_kernel", "lpc_coefficients_kernel", "choose_kernel", "encode_frames_kernel"]
+        stage_names = ["analyse_kernel", "lpc_coefficients_kernel", "choose_kernel", "serialise_kernel"]
         dom = int(np.argmax(stages))
         # every stage but the coefficient kernel reads the step's PCM once; the serialising kernel
         # also writes the stream, the others a few hundred bytes per subframe (not counted)
@@ -727,7 +727,7 @@ def main():
             "frames_outside_reference_domain": int(st.out_of_domain),
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload) if args.seconds is None else None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(args.workload, stage_names[dom]) if args.seconds is None else None, "peak_source": peak_src,
                          "kernel": stage_names[dom], "kernel_ms": stages[dom], "algorithmic_bytes": int(dom_algo),
                          "stages_ms": dict(zip(stage_names, stages)), "stages_sum_ms": float(sum(stages)),
                          "stages_measured": "separate steps with an event between the stages (FLACB_STAGE_TIMES); the timed steps overlap them",
