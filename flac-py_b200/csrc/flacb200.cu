@@ -1100,10 +1100,10 @@ static int decode_frames_impl(flacb_ctx *c, const uint8_t *frames, uint64_t len,
     int32_t *d_tmp = (int32_t *)c->d_frames.p;
     /* D3 + D4 */
     /* Frames per warp.  A lane's walk through its frame is a chain of dependent instructions: few frames per warp
-     * mean many warps to hide it behind, until the schedulers are full (about ten warps per SM: config 2's 5743
-     * frames are fastest at 4 lanes, config 3's 21094 at 16). */
+     * mean many warps to hide it behind, until the schedulers are full (about a dozen warps per SM: config 2's
+     * 5743 frames among 6919 candidates are fastest at 4 lanes, config 3's 21094 frames at 16). */
     int lanes = 2;
-    while (lanes < 32 && n_cand > (u64)lanes * (u64)c->sm_count * 10u) lanes *= 2;
+    while (lanes < 32 && n_cand > (u64)lanes * (u64)c->sm_count * 12u) lanes *= 2;
     if (const char *e = getenv("FLACB200_DECODE_LANES")) { /* tuning knob */
         const int v = atoi(e);
         if (v >= 1 && v <= 32) lanes = v;
