@@ -354,6 +354,7 @@ struct Shared {
     int chan_status[MAX_CH]; /* first error of each channel, in the reference's evaluation order */
     int32_t warm[MAX_CH][FLACB_MAX_LPC]; /* warm-up samples (the planes become residuals) */
     int cur_ch;
+    uint32_t wmax_hi; /* autocorrelation: high word of the largest |windowed sample| of the tapered ends (0 between uses) */
     uint32_t cand_o[MAX_CAND], cand_magic[MAX_CAND];
     uint32_t sizeA[MAX_CAND], sizeB[MAX_CAND], any5[MAX_CAND];
     uint32_t errkey;
@@ -788,10 +789,16 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
         /* The last sample never enters a product (encoder.py:449, range(len - lag - 1): neither as the
          * left nor as the right factor), and there are zeros behind it: with w[n - 1] stored as zero
          * no product needs a range check.  (Adding a zero product changes neither part of a sum.) */
+        uint32_t mhi = 0;
         for (int t = b.tid; t < count; t += b.B) {
             const int i = t < A ? t : Bq + (t - A);
-            wxs[t + (t >> 3)] = i >= n - 1 ? 0.0 : __dmul_rn((double)x[swz((uint32_t)(GUARD + i))], b.win[i]);
+            const double w = i >= n - 1 ? 0.0 : __dmul_rn((double)x[swz((uint32_t)(GUARD + i))], b.win[i]);
+            wxs[t + (t >> 3)] = w;
+            const uint32_t hi = (uint32_t)__double2hiint(w) & 0x7FFFFFFFu; /* |w|'s high word: monotone in |w| */
+            mhi = hi > mhi ? hi : mhi;
         }
+        mhi = __reduce_max_sync(FULL, mhi);
+        if (b.lane == 0 && mhi) atomicMax(&b.sh.wmax_hi, mhi);
         __syncthreads();
         /* The tapered runs (everything autoc_flat() refuses) are the runs [0, RA) and [RB, nruns),
          * T of them: thread t takes the runs number t, t + B, ... of that list, Q each -- and the
@@ -814,10 +821,23 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
             const int i0 = (tau < RA ? tau : RB + (tau - RA)) * E;
             return i0 < A ? i0 : A + (i0 - Bq);
         };
+        /* A thread's sum of one lag is kept against a bias 1.5 * 2^k with 2^(k-1) above anything the sum can
+         * reach (k from the largest |w| of the frame's tapered ends and the thread's number of products): every
+         * a + p then rounds to the same fixed grid, the part of p that a took, (a + p) - a, is exact, and so
+         * is the rest p - that (a's rounding error; |a| > |p|: three operations where the symmetric TwoSum
+         * needs six).  The rests are far below the grid and add up in an ordinary double, as the error
+         * terms of the double-double form did.  (sum, rests) leave the loop as the same kind of pair. */
+        const uint32_t wm = b.sh.wmax_hi;
+        double bias = 1.5;
+        if ((wm >> 20) != 0) {
+            const int nprod = (Q + 1) * E;
+            const int k = 2 * ((int)(wm >> 20) - 1023 + 1) + (32 - __clz(nprod)) + 1;
+            bias = __hiloint2double((int)(((uint32_t)(k + 1023) << 20) | 0x80000u), 0);
+        }
         for (int lag0 = 0; lag0 <= L; lag0 += LG) {
             double s[LG], c[LG];
 #pragma unroll
-            for (int l = 0; l < LG; l++) s[l] = 0.0, c[l] = 0.0;
+            for (int l = 0; l < LG; l++) s[l] = bias, c[l] = 0.0;
             for (int tau = b.tid; tau < Tmain; tau += b.B) {
                 const int t0 = run_pos(tau); /* a thread's reads stay inside one range */
                 double wa[E], wb[E + LG - 1];
@@ -829,10 +849,17 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
                 for (int l = 0; l < LG; l++) {
                     if (lag0 + l <= L) {
 #pragma unroll
-                        for (int e = 0; e < E; e++) dd_add(s[l], c[l], __dmul_rn(wa[e], wb[e + l]));
+                        for (int e = 0; e < E; e++) {
+                            const double pr = __dmul_rn(wa[e], wb[e + l]);
+                            const double t = __dadd_rn(s[l], pr);
+                            c[l] = __dadd_rn(c[l], __dsub_rn(pr, __dsub_rn(t, s[l])));
+                            s[l] = t;
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int l = 0; l < LG; l++) s[l] = __dsub_rn(s[l], bias);
             warp_sum4(s, c, lag0);
         }
         if (R) {
@@ -907,6 +934,7 @@ __device__ void autocorrelation(Blk &b, const int32_t *x, int L)
         }
         if (b.lane == 0) b.autoc[lag] = __dadd_rn(S, C);
     }
+    if (b.tid == 0) b.sh.wmax_hi = 0; /* for the next channel: every thread has read it long ago */
     __syncthreads();
 }
 
@@ -1997,6 +2025,7 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
 #endif
     }
     if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
+    if (b.tid == 0) sh.wmax_hi = 0;
     b.n = (f == p.n_frames - 1) ? p.tail_size : p.block_size;
     b.ntiles = (b.n + b.B * E - 1) / (b.B * E);
     const SmemLayout &lay = p.lay;
@@ -2151,6 +2180,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
     b.stg_words = lay.stg_words;
     b.wx_bytes = lay.kall - lay.res;
     if (b.tid < MAX_CH) sh.chan_status[b.tid] = 0;
+    if (b.tid == 0) sh.wmax_hi = 0;
 
     /* ---- phase 0 + 1 ---- */
     if (lay.xs_all) load_planes(b, -1);
