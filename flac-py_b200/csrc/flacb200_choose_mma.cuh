@@ -199,7 +199,7 @@ __device__ void lpc_errors_mma(Blk &b, const uint8_t *bpl, uint32_t bstride, int
 #pragma unroll
                             for (int p = NP - 2; p >= 1; p--) hi = (hi << 8) + c[p][2 * r + j];
                             const i64 pred = NP > 1 ? (i64)hi * 256 + (i64)c[0][2 * r + j] : (i64)hi;
-                            t32 += (uint32_t)abs(xr[r] - (int)(uint32_t)(u64)(pred >> shift[nt][j]));
+                            t32 = __sad(xr[r], (int)(uint32_t)(u64)(pred >> shift[nt][j]), t32);
                         }
                         acc[nt][j] += (u64)t32;
                     }

@@ -669,15 +669,28 @@ static __device__ void fixed_errors(Blk &b, const int32_t *x)
         if (i0 < b.n) {
             int a[E + 4];
             ld_run<E + 4>(x, (uint32_t)(GUARD + i0 - 4), a);
+            if (i0 >= 4 && i0 + E <= b.n) { /* nothing to mask; |r| < 2^28 (bits <= 24): a run's eight fit 32 bits */
+                uint32_t t32[5] = {0, 0, 0, 0, 0};
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const int i = i0 + e;
-                if (i < b.n) {
+                for (int e = 0; e < E; e++) {
                     int r[5];
                     fixed_residuals(a, e, r);
 #pragma unroll
-                    for (int o = 0; o < 5; o++)
-                        if (i >= o) acc[o] += (u64)(uint32_t)(r[o] < 0 ? -r[o] : r[o]);
+                    for (int o = 0; o < 5; o++) t32[o] = __sad(r[o], 0, t32[o]); /* |r| + t: one instruction */
+                }
+#pragma unroll
+                for (int o = 0; o < 5; o++) acc[o] += (u64)t32[o];
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int i = i0 + e;
+                    if (i < b.n) {
+                        int r[5];
+                        fixed_residuals(a, e, r);
+#pragma unroll
+                        for (int o = 0; o < 5; o++)
+                            if (i >= o) acc[o] += (u64)(uint32_t)(r[o] < 0 ? -r[o] : r[o]);
+                    }
                 }
             }
         }
@@ -1047,16 +1060,23 @@ static inline int __dp2a_hi(int a, int bq, int c)
 
 /* sum |x[i] - (pred >> shift)| over the thread's E samples; lo/hi: first / one past the last valid
  * sample of the run (0 / E for interior runs) */
-template <class ACC>
+template <class ACC, bool TIGHT = false>
 __device__ __forceinline__ u64 lpc_abs_sum(const int (&xe)[E], const ACC (&acc)[E], int shift, bool interior, int lo, int hi)
 {
     u64 tot = 0;
-    if (sizeof(ACC) == 4 && interior) {
+    if (sizeof(ACC) == 4 && interior && TIGHT) {
+        /* 16-bit samples against coefficient bytes: |r| < 2^28, the run's eight fit 32 bits; |a - b| + c is
+         * one instruction (VABSDIFF) */
+        uint32_t t32 = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) t32 = __sad(xe[e], (int)(acc[e] >> shift), t32);
+        tot = t32;
+    } else if (sizeof(ACC) == 4 && interior) {
 #pragma unroll
         for (int e = 0; e < E; e += 2) { /* |r| < 2^31 each: pairs fit 32 bits */
-            const int r0 = xe[e] - (int)(acc[e] >> shift);
-            const int r1 = xe[e + 1] - (int)(acc[e + 1] >> shift);
-            tot += (u64)((uint32_t)abs(r0) + (uint32_t)abs(r1));
+            uint32_t t32 = __sad(xe[e], (int)(acc[e] >> shift), 0u);
+            t32 = __sad(xe[e + 1], (int)(acc[e + 1] >> shift), t32);
+            tot += (u64)t32;
         }
     } else {
 #pragma unroll
@@ -1112,7 +1132,7 @@ __device__ __forceinline__ u64 lpc_body_dp2a(const int (&pk)[LMAX + E - 1], cons
             acc[e] = __dp2a_hi(pk[LMAX + e - 4 - 4 * t4], cw, acc[e]);
         }
     }
-    return lpc_abs_sum<int>(xe, acc, shift, interior, lo, hi);
+    return lpc_abs_sum<int, true>(xe, acc, shift, interior, lo, hi);
 }
 
 template <int LMAX, int FLAVOUR>

@@ -298,6 +298,7 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline unsigned __sad(int a, int b, unsigned c) { const long long d = (long long)a - (long long)b; return c + (unsigned)(d < 0 ? -d : d); }
 static inline int __double2hiint(double a) { long long v; memcpy(&v, &a, 8); return (int)(v >> 32); }
 static inline double __hiloint2double(int hi, int lo) { long long v = ((long long)hi << 32) | (unsigned)lo; double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double2ll_rd(double a) { return (long long)floor(a); }
