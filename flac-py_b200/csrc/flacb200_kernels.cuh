@@ -671,12 +671,22 @@ static __device__ void fixed_errors(Blk &b, const int32_t *x)
             ld_run<E + 4>(x, (uint32_t)(GUARD + i0 - 4), a);
             if (i0 >= 4 && i0 + E <= b.n) { /* nothing to mask; |r| < 2^28 (bits <= 24): a run's eight fit 32 bits */
                 uint32_t t32[5] = {0, 0, 0, 0, 0};
+                /* the predictors are successive differences (common.py:15-21 are the binomial rows): four
+                 * subtractions per sample serve all five orders; the last difference goes into |a - b| + t */
+                int r1[E + 3], r2[E + 2], r3[E + 1];
+#pragma unroll
+                for (int j = 0; j < E + 3; j++) r1[j] = a[j + 1] - a[j];
+#pragma unroll
+                for (int j = 0; j < E + 2; j++) r2[j] = r1[j + 1] - r1[j];
+#pragma unroll
+                for (int j = 0; j < E + 1; j++) r3[j] = r2[j + 1] - r2[j];
 #pragma unroll
                 for (int e = 0; e < E; e++) {
-                    int r[5];
-                    fixed_residuals(a, e, r);
-#pragma unroll
-                    for (int o = 0; o < 5; o++) t32[o] = __sad(r[o], 0, t32[o]); /* |r| + t: one instruction */
+                    t32[0] = __sad(a[e + 4], 0, t32[0]); /* |r| + t: one instruction */
+                    t32[1] = __sad(r1[e + 3], 0, t32[1]);
+                    t32[2] = __sad(r2[e + 2], 0, t32[2]);
+                    t32[3] = __sad(r3[e + 1], 0, t32[3]);
+                    t32[4] = __sad(r3[e + 1], r3[e], t32[4]);
                 }
 #pragma unroll
                 for (int o = 0; o < 5; o++) acc[o] += (u64)t32[o];

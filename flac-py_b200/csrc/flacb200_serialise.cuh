@@ -466,8 +466,8 @@ __device__ __forceinline__ void size_channel(SerCtx &b, int c)
                     uint32_t t[5] = {0, 0, 0, 0, 0};
 #pragma unroll
                     for (int e = e0; e < e0 + 4; e++) {
-                        t[0] += (uint32_t)abs(a[e + 4]), t[1] += (uint32_t)abs(r1[e + 3]), t[2] += (uint32_t)abs(r2[e + 2]);
-                        t[3] += (uint32_t)abs(r3[e + 1]), t[4] += (uint32_t)abs(r4[e]);
+                        t[0] = __sad(a[e + 4], 0, t[0]), t[1] = __sad(r1[e + 3], 0, t[1]), t[2] = __sad(r2[e + 2], 0, t[2]);
+                        t[3] = __sad(r3[e + 1], 0, t[3]), t[4] = __sad(r3[e + 1], r3[e], t[4]); /* |a - b| + t: one instruction */
                     }
 #pragma unroll
                     for (int o = 0; o < 5; o++) acc[o] += t[o];
