@@ -313,6 +313,8 @@ def api_and_cli(name: str, m: dict, raw: np.ndarray, flac_bytes: int) -> dict:
                 secs = float(printed[-1].split("completed in")[1].split()[0]) if printed else None
                 rec[action] = {"printed_s": secs, "process_wall_s": wall, "rc": r.returncode,
                                "Msamples_per_s_printed": n * ch / secs / 1e6 if secs else None}
+                if r.returncode != 0:
+                    rec[action]["stderr_tail"] = r.stderr[-400:]
             with wave.open(back, "rb") as w:
                 same = w.readframes(w.getnframes()) == payload
             rec["flac_bytes"] = os.path.getsize(flac)

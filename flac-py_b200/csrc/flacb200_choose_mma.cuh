@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(TB, MINB) choose_mma_kernel(const EncParams p,
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
+    FLACB_SIM_POISON(sh);
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = (int)blockDim.x;

@@ -44,6 +44,7 @@
 #else
 #include <cuda_runtime.h>
 #define FLACB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define FLACB_SIM_POISON(obj) ((void)0) /* the CPU simulator poisons static shared memory here */
 #endif
 
 #include "../../include/flacb200.h"
@@ -1989,6 +1990,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
+    FLACB_SIM_POISON(sh);
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = FIXB ? FIXB : (int)blockDim.x; /* FIXB: the block size as a compile-time constant (the usual 288) */
@@ -1999,6 +2001,7 @@ __global__ void __launch_bounds__(TB, MINB) analyse_kernel(const EncParams p)
     pdl_launch_dependents(); /* stage B's CTAs may come in behind this stage's last ones */
     if (b.tid == 0) {
         sh.frame = f;
+        sh.wmax_hi = 0;
 #ifdef FLACB_PHASE_TIMING
         sh.t_last = clock64();
 #endif
@@ -2041,6 +2044,7 @@ __global__ void __launch_bounds__(TB, MINB) choose_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
+    FLACB_SIM_POISON(sh);
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = FIXB ? FIXB : (int)blockDim.x;
@@ -2121,6 +2125,7 @@ __global__ void __launch_bounds__(128) lpc_coefficients_kernel(const EncParams p
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
+    FLACB_SIM_POISON(sh);
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = (int)blockDim.x;
@@ -2159,6 +2164,7 @@ __global__ void __launch_bounds__(TB, MINB) encode_frames_kernel(const EncParams
 {
     FLACB_DYN_SMEM(smem);
     __shared__ Shared sh;
+    FLACB_SIM_POISON(sh);
     Blk b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = FIXB ? FIXB : (int)blockDim.x;

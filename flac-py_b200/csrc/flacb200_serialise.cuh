@@ -886,6 +886,7 @@ __global__ void __launch_bounds__(TB, MINB) serialise_kernel(const EncParams p)
 {
     FLACB_DYN_SMEM(smem);
     __shared__ SerShared sh;
+    FLACB_SIM_POISON(sh);
     SerCtx b(p, sh);
     b.tid = (int)threadIdx.x;
     b.B = (int)blockDim.x;

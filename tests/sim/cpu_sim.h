@@ -56,6 +56,7 @@ struct State {
     unsigned wbar_gen[64];
     unsigned long long wbuf[64][32];
     unsigned char *dyn_smem = nullptr, *dyn_alloc = nullptr;
+    unsigned long long block_serial = 0; /* CTAs run so far */
     std::function<void()> body;
 };
 
@@ -142,6 +143,7 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
 {
     State &s = st();
     const size_t stack_bytes = 256 * 1024;
+    s.block_serial++;
     s.nthreads = nthreads;
     s.bar_count = 0;
     memset(s.nbar_count, 0, sizeof(s.nbar_count));
@@ -213,6 +215,16 @@ inline void run_block(unsigned block, unsigned grid, int nthreads, size_t dyn_sm
 #define gridDim sim::g_gridDim
 
 #define FLACB_DYN_SMEM(name) unsigned char *name = sim::st().dyn_smem
+/* statically allocated shared memory of a kernel (a function-local static here) is poisoned by the first
+ * thread of every CTA to get there: on the device it holds whatever the CTA before left behind */
+#define FLACB_SIM_POISON(obj)                                   \
+    do {                                                        \
+        static unsigned long long done_ = 0;                    \
+        if (done_ != sim::st().block_serial) {                  \
+            done_ = sim::st().block_serial;                     \
+            memset((void *)&(obj), 0xA5, sizeof(obj));          \
+        }                                                       \
+    } while (0)
 
 static inline void __syncthreads() { sim::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { sim::syncwarp(); }

@@ -295,3 +295,21 @@ def test_sim_tensor_core_filter_64_bit_path(name, monkeypatch):
     monkeypatch.setenv("FLACB_SIM_MMA_WIDE", "1")
     a = simlib.encode_frames(x, case["bits"], plane_mode=3 << 9, **case_kwargs(case))
     assert a[0] == 0 and a[1] == case_stream(case)[42:]
+
+
+@pytest.mark.parametrize("bits,block,L,channels,frames", [(16, 4608, 12, 2, 12), (24, 4096, 32, 2, 4)])
+def test_sim_autocorrelation_bits_match_the_oracle_over_many_frames(bits, block, L, channels, frames):
+    """every lag of every subframe of a run of frames of the bench's mixed signal, bit pattern against bit
+    pattern (the reference's compensated sum() is the correctly rounded exact sum; encoder.py:443-450).  Several
+    CTAs in a row with the simulator's poisoned static shared memory: state a frame must not inherit from the
+    frame before (a stale per-frame maximum once cost 1 lag in 200 its last bit on the GPU only)."""
+    import flacb200_synth as S
+    x = S.pcm(frames * block, channels, bits, 44100, "mixed", 1234, start=0)
+    ref = O.encode_frames(x, bits, block, L, 5, 0, 5, want_info=True)
+    rc, data, _, info, _ = simlib.encode_frames(x, bits, block, L, 5, 0, 5, want_info=True)
+    assert rc == 0 and data == ref.data
+    bad = 0
+    for a, r in zip(info, ref.info):
+        for lag in range(L + 1):
+            bad += np.float64(a.autoc[lag]).tobytes() != np.float64(r.autoc[lag]).tobytes()
+    assert bad == 0
