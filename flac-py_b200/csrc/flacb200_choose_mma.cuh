@@ -252,7 +252,21 @@ static __device__ __noinline__ void load_byte_planes(const uint8_t *base, uint8_
         bpl[(uint32_t)p * bstride + (uint32_t)(j < MMA_GB ? j : n + j)] = 0;
     }
     const bool aligned = (((uintptr_t)base) & (uintptr_t)(cbytes - 1)) == 0 || cbytes == 3 || cbytes == 1;
-    for (int i = tid; i < n; i += B) {
+    /* four samples per thread and round: the loads of a round are issued together (one after the other they each
+     * waited for HBM), and a round's bytes of a plane leave as one 32-bit store */
+    const int n4 = n & ~3;
+    for (int i = 4 * tid; i < n4; i += 4 * B) {
+        int32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = load_sample(base, (u64)(i + k) * (u64)channels + (u64)c, cbytes, 0, aligned);
+        for (int p = 0; p < planes; p++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) w |= (((uint32_t)v[k] >> (8 * p)) & 0xFFu) << (8 * k);
+            *(uint32_t *)(bpl + (uint32_t)p * bstride + (uint32_t)(MMA_GB + i)) = w;
+        }
+    }
+    for (int i = n4 + tid; i < n; i += B) {
         const int32_t v = load_sample(base, (u64)i * (u64)channels + (u64)c, cbytes, 0, aligned);
         for (int p = 0; p < planes; p++) bpl[(uint32_t)p * bstride + (uint32_t)(MMA_GB + i)] = (uint8_t)((uint32_t)v >> (8 * p));
     }
