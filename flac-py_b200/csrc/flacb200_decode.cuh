@@ -608,6 +608,16 @@ __device__ __forceinline__ void rice_fast(LaneState &st)
     if ((u64)n > (words_left - 3) / 2) n = (int)((words_left - 3) / 2);
     if (n <= 0) return;
     uint32_t o = (uint32_t)(bitpos - (u64)wbyte * 8);
+    /* The word fetched ahead is used one refill later (about a code): enough for a line that is in L1, not for
+     * one that has to come from L2 or HBM -- and with several lanes per warp some lane starts a new line in
+     * every third iteration, and the whole warp waits (28 % of the kernel's stall samples).  So the lines a
+     * burst or two ahead are asked for now. */
+#ifndef FLACB_CPU_SIM
+    if ((u64)wbyte + 512 <= g.len) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"((const uint8_t *)wp + 128));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"((const uint8_t *)wp + 256));
+    }
+#endif
     uint32_t w0 = __byte_perm(wp[0], 0, 0x0123), w1 = __byte_perm(wp[1], 0, 0x0123), pre = wp[2];
     wp += 3;
     int32_t *out = st.out + st.pos;
