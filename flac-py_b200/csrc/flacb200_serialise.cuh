@@ -330,15 +330,18 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
         if (head > nbytes) head = nbytes;
         const uint32_t nq = (nbytes - head) >> 2;
         const uint32_t tail0 = head + nq * 4u;
+#pragma unroll 1
         for (uint32_t idx = (uint32_t)tid; idx < head + (nbytes - tail0); idx += (uint32_t)B) {
             const uint32_t i = idx < head ? idx : tail0 + (idx - head);
             dst[i] = (uint8_t)(stg[i >> 2] >> (24u - 8u * (i & 3u)));
         }
         uint32_t *dstw = (uint32_t *)(dst + head);
         if (head == 0) {
+#pragma unroll 2
             for (uint32_t q = (uint32_t)tid; q < nq; q += (uint32_t)B) dstw[q] = __byte_perm(stg[q], 0, 0x0123);
         } else {
             const uint32_t sh8 = 8u * head;
+#pragma unroll 2
             for (uint32_t q = (uint32_t)tid; q < nq; q += (uint32_t)B) {
                 /* bytes head + 4q .. + 3 of the window: the low (4 - head) bytes of word q, the high `head` bytes of word q + 1 */
                 const uint32_t big = (stg[q] << sh8) | (stg[q + 1] >> (32u - sh8));
@@ -356,6 +359,7 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
         if (w0 >= nwords && !tail_owner) return;
         const uint32_t w1 = w0 >= nwords ? w0 : (w0 + sw < nwords ? w0 + sw : nwords);
         uint32_t c = 0;
+#pragma unroll 2
         for (uint32_t q = w0; q < w1; q++) {
             const uint32_t v = stg[q] ^ (c << 16);
             c = (uint32_t)sh.crc4[3][v >> 24] ^ (uint32_t)sh.crc4[2][(v >> 16) & 255u] ^ (uint32_t)sh.crc4[1][(v >> 8) & 255u] ^
@@ -363,6 +367,7 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
         }
         uint32_t hi_byte = w1 * 4u;
         if (tail_owner) {
+#pragma unroll 1
             for (uint32_t idx = nwords * 4u; idx < nbytes; idx++) {
                 const uint32_t byte = (stg[idx >> 2] >> (24u - 8u * (idx & 3u))) & 0xFFu;
                 c = ((c << 8) ^ (uint32_t)sh.crc4[0][(c >> 8) ^ byte]) & 0xFFFFu;
@@ -390,6 +395,7 @@ static __device__ __noinline__ void flush_v2(SerShared *shp, uint32_t *stg, uint
     const uint32_t carry_idx = wend - sh.wbase;
     const uint32_t carry = carry_idx < stg_words + 4u ? stg[carry_idx] : 0u;
     __syncthreads();
+#pragma unroll 1
     for (uint32_t idx = (uint32_t)tid; idx < stg_words + 4u; idx += (uint32_t)B) stg[idx] = idx == 0 ? carry : 0u;
     if (tid == 0) sh.wbase = wend;
     __syncthreads();
