@@ -202,7 +202,7 @@ inline LaunchShape pick_shape(int block_size, int e, size_t static_smem, size_t 
  * chunk, taken as it is; edge_override > 0 (FLACB200_EDGE_CHUNK_FRAMES): size of the first and
  * last chunk. */
 inline std::vector<uint64_t> chunk_plan(uint64_t n_frames, uint64_t wave, uint64_t frame_pcm, long long want_override,
-                                        long long edge_override)
+                                        long long edge_override, long long last_override = 0)
 {
     std::vector<uint64_t> f0;
     f0.push_back(0);
@@ -219,6 +219,7 @@ inline std::vector<uint64_t> chunk_plan(uint64_t n_frames, uint64_t wave, uint64
     if (want * 2 <= n_frames) {
         uint64_t first = edge, last = edge;
         if (edge_override > 0) first = last = (uint64_t)edge_override;
+        if (last_override > 0) last = (uint64_t)last_override;
         if (first + last >= n_frames) first = last = want;
         uint64_t f = first < want ? first : want;
         while (f + last < n_frames) {

@@ -261,9 +261,9 @@ extern "C" int flacb_sim_encode(const void *pcm, uint64_t n_sample_frames, int c
 
 /* the chunk plan of the host path (flacb200_host.h), for the host-logic tests */
 extern "C" int flacb_sim_chunk_plan(uint64_t n_frames, uint64_t wave, uint64_t frame_pcm, long long want_override,
-                                    long long edge_override, uint64_t *out, int cap)
+                                    long long edge_override, long long last_override, uint64_t *out, int cap)
 {
-    const std::vector<uint64_t> f0 = chunk_plan(n_frames, wave, frame_pcm, want_override, edge_override);
+    const std::vector<uint64_t> f0 = chunk_plan(n_frames, wave, frame_pcm, want_override, edge_override, last_override);
     for (size_t i = 0; i < f0.size() && (int)i < cap; i++) out[i] = f0[i];
     return (int)f0.size();
 }

@@ -156,14 +156,14 @@ def decode_frames(frames: bytes, streaminfo_bits: int, cap_samples: int | None =
     return rc, out[:n.value * f].reshape(-1, f).copy(), fch.value, nc.value
 
 
-def chunk_plan(n_frames: int, wave: int, frame_pcm: int, want: int = 0, edge: int = 0) -> list[int]:
+def chunk_plan(n_frames: int, wave: int, frame_pcm: int, want: int = 0, edge: int = 0, last: int = 0) -> list[int]:
     """first frame of every chunk of the host path, then n_frames (flacb200_host.h chunk_plan)"""
     L = lib()
     L.flacb_sim_chunk_plan.restype = C.c_int
-    L.flacb_sim_chunk_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_longlong, C.c_longlong,
+    L.flacb_sim_chunk_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_longlong, C.c_longlong, C.c_longlong,
                                        C.POINTER(C.c_uint64), C.c_int]
     cap = int(n_frames) + 2
     buf = (C.c_uint64 * cap)()
-    n = L.flacb_sim_chunk_plan(n_frames, wave, frame_pcm, want, edge, buf, cap)
+    n = L.flacb_sim_chunk_plan(n_frames, wave, frame_pcm, want, edge, last, buf, cap)
     assert n <= cap
     return [int(buf[i]) for i in range(n)]

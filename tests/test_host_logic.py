@@ -183,12 +183,16 @@ def test_chunk_plan_of_the_host_path():
     # config 3: waves of 148 big frames: two waves per chunk
     sizes = [b - a for a, b in zip(*(lambda q: (q[:-1], q[1:]))(simlib.chunk_plan(3516, 148, 16384 * 2 * 3)))]
     assert sizes[0] == 148 and sizes[-1] == 148 and 296 in sizes
+    # LPC configurations: a third of a wave first, two thirds last (what flacb_encode_pcm asks for)
+    p = simlib.chunk_plan(5743, 444, 4608 * 2 * 2, 0, 148, 296)
+    sizes = [b - a for a, b in zip(p[:-1], p[1:])]
+    assert p[0] == 0 and p[-1] == 5743 and sizes[0] == 148 and sizes[-1] == 296 and set(sizes[1:-2]) == {888}
     for n in (1, 2, 71, 443, 444, 887, 888, 889, 1333, 5743, 100001):
         for wave in (1, 148, 444):
             for pcm in (64, 18432, 110592):
-                for want, edge in ((0, 0), (5, 0), (16, 0), (100000, 0), (888, 7)):
-                    q = simlib.chunk_plan(n, wave, pcm, want, edge)
-                    assert q[0] == 0 and q[-1] == n and all(b > a for a, b in zip(q[:-1], q[1:])), (n, wave, pcm, want, edge, q[:6])
+                for want, edge, last in ((0, 0, 0), (5, 0, 0), (16, 0, 0), (100000, 0, 0), (888, 7, 0), (0, 49, 98), (0, 148, 296)):
+                    q = simlib.chunk_plan(n, wave, pcm, want, edge, last)
+                    assert q[0] == 0 and q[-1] == n and all(b > a for a, b in zip(q[:-1], q[1:])), (n, wave, pcm, want, edge, last, q[:6])
 
 
 def test_data_model_records_match_the_reference_names_and_tables():
