@@ -654,7 +654,7 @@ __device__ __forceinline__ void rice_fast(LaneState &st)
 /* frames per warp: fewer than 32 trades idle lanes for less divergence between the lanes' states
  * and more warps per SM (the kernel is bound by the latency of one lane's instruction stream:
  * refill, count zeros, shift, read k bits, store) */
-constexpr int DECODE_LANES = 8;  /* default; the launch passes the value in use */
+constexpr int DECODE_LANES = 8;  /* the simulator's value; the library picks 2..32 from the number of candidates (flacb200.cu) */
 constexpr int DECODE_WARPS = 4;  /* warps per CTA */
 
 __global__ void __launch_bounds__(32 * DECODE_WARPS) decode_frames_kernel(const uint8_t *s, u64 len, Candidate *cand, uint32_t n_cand,
