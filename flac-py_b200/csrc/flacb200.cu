@@ -805,6 +805,29 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
         pd.active = false;
         CUDA_TRY(cudaStreamSynchronize(sl.stream));
         if (timeline) fprintf(stderr, "host: chunk f0=%llu kernels seen done at %.3f\n", (unsigned long long)pd.f0, host_ms());
+        /* first things first: the chunk's size is on the host now, so its output copy can start; the
+         * bookkeeping (a dozen event queries, the offsets) follows while it runs -- for the last chunk of a call
+         * nothing else hides it */
+        const bool discard = status != FLACB_OK; /* an earlier chunk already failed */
+        int64_t bad = -1;
+        u64 valid = 0;
+        int st = FLACB_OK;
+        bool nospace = false;
+        if (!discard) {
+            st = first_bad(pd.meta, pd.nfr, flags, bad, valid);
+            if (host_out) {
+                if (host_off + valid > out_cap) nospace = true;
+                else if (valid) {
+                    const double h0 = host_ms();
+                    /* the chunk's kernels are done (the host has just waited for them) */
+                    CUDA_TRY(cudaEventRecord(sl.ev_d0, c->d2h_stream));
+                    CUDA_TRY(cudaMemcpyAsync(out + host_off, sl.out.p, valid, cudaMemcpyDeviceToHost, c->d2h_stream));
+                    CUDA_TRY(cudaEventRecord(sl.ev_d1, c->d2h_stream));
+                    if (timeline) fprintf(stderr, "host: d2h of chunk f0=%llu enqueued %.3f-%.3f\n", (unsigned long long)pd.f0, h0, host_ms());
+                    sl.d2h_pending = true;
+                }
+            }
+        }
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1));
         k_ms += ms;
@@ -827,10 +850,7 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
             CUDA_TRY(cudaEventElapsedTime(&ms, sl.ev_c0, sl.ev_c1));
             h2d_ms += ms;
         }
-        if (status != FLACB_OK) return FLACB_OK; /* an earlier chunk already failed: discard */
-        int64_t bad;
-        u64 valid;
-        const int st = first_bad(pd.meta, pd.nfr, flags, bad, valid);
+        if (discard) return FLACB_OK;
         if (frame_offsets)
             for (u64 f = 0; f <= pd.nfr; f++) frame_offsets[pd.f0 + f] = host_off + pd.meta.h_frame_off[f];
         for (int o = 0; o < 6; o++) hist[o] += pd.meta.h_stats[o];
@@ -846,21 +866,10 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
 #endif
         ood += pd.meta.h_stats[6];
         threads = pd.meta.threads, smem = pd.meta.smem;
-        if (host_out) {
-            if (host_off + valid > out_cap) {
-                status = st != FLACB_OK ? st : FLACB_E_NOSPACE;
-                bad_frame = (int64_t)pd.f0 + (bad >= 0 ? bad : 0);
-                return FLACB_OK;
-            }
-            if (valid) {
-                const double h0 = host_ms();
-                /* the chunk's kernels are done (the host has just waited for them) */
-                CUDA_TRY(cudaEventRecord(sl.ev_d0, c->d2h_stream));
-                CUDA_TRY(cudaMemcpyAsync(out + host_off, sl.out.p, valid, cudaMemcpyDeviceToHost, c->d2h_stream));
-                CUDA_TRY(cudaEventRecord(sl.ev_d1, c->d2h_stream));
-                if (timeline) fprintf(stderr, "host: d2h of chunk f0=%llu enqueued %.3f-%.3f\n", (unsigned long long)pd.f0, h0, host_ms());
-                sl.d2h_pending = true;
-            }
+        if (nospace) {
+            status = st != FLACB_OK ? st : FLACB_E_NOSPACE;
+            bad_frame = (int64_t)pd.f0 + (bad >= 0 ? bad : 0);
+            return FLACB_OK;
         }
         host_off += valid;
         if (st != FLACB_OK) {
