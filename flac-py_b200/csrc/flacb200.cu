@@ -25,6 +25,15 @@ using namespace flacb;
 static thread_local std::string g_cuda_error;
 static std::atomic<uint64_t> g_launches{0};
 
+/* Clears a call's counters, statuses and look-back words.  A kernel and not cudaMemsetAsync: on the host path the
+ * memset queued up on a copy engine behind another chunk's input or output copy (60 us between the end of a chunk's
+ * input copy and its first kernel on the call's timeline). */
+__global__ void zero_words_kernel(unsigned long long *p, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0ull;
+}
+
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
         cudaError_t e_ = (expr);                                                               \
@@ -583,7 +592,11 @@ static int launch_encode(flacb_ctx *c, EncSlot &sl, const EncPlan &plan, const u
         }
         return FLACB_OK;
     };
-    CUDA_TRY(cudaMemsetAsync(dmeta + o_misc, 0, o_lb + n_frames * 8 - o_misc, sl.stream)); /* counters, statuses, look-back words */
+    {   /* counters, statuses, look-back words (o_misc and the length are multiples of 8) */
+        const uint64_t words = (o_lb + n_frames * 8 - o_misc) / 8;
+        if (getenv("FLACB200_MEMSET")) CUDA_TRY(cudaMemsetAsync(dmeta + o_misc, 0, words * 8, sl.stream));
+        else zero_words_kernel<<<(unsigned)((words + 255) / 256), 256, 0, sl.stream>>>((unsigned long long *)(dmeta + o_misc), words);
+    }
     CUDA_TRY(cudaEventRecord(sl.ev_k0, sl.stream));
     sl.staged = !plan.staged ? 0 : stage_times ? 1 : 2;
     if (plan.staged) {
@@ -905,6 +918,33 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
         const int v = atoi(e);
         if (v >= 1 && v < FLACB_SLOTS) ahead = v;
     }
+    /* The input copies are what the call waits for (the link is slower than the kernels), so the copy of chunk
+     * ci + 1 is queued as soon as its slot's input buffer is free -- before the host goes to wait for an older
+     * chunk's kernels -- and not when the loop gets to it: the copy engine never runs dry. */
+    std::vector<char> h2d_issued(n_chunks, 0);
+    auto chunk_span = [&](u64 cj, u64 &f0, u64 &nfr, u64 &s0, u64 &ns) {
+        f0 = chunk_f0[cj];
+        nfr = chunk_f0[cj + 1] - f0;
+        s0 = f0 * (u64)block_size;
+        ns = (f0 + nfr == n_frames) ? n_sample_frames - s0 : nfr * (u64)block_size;
+    };
+    auto issue_h2d = [&](u64 cj) -> int {
+        if (!host_in || cj >= n_chunks || h2d_issued[cj]) return FLACB_OK;
+        const int sj = (int)(cj % FLACB_SLOTS);
+        if (pend[sj].active) return FLACB_OK; /* the kernels of the slot's chunk may still read its input: later */
+        EncSlot &sl = c->slot[sj];
+        u64 f0, nfr, s0, ns;
+        chunk_span(cj, f0, nfr, s0, ns);
+        const u64 nb = ns * (u64)channels * (u64)cbytes;
+        int rc2;
+        if ((rc2 = sl.pcm.ensure(nb))) return rc2;
+        if (timeline) fprintf(stderr, "host: h2d of chunk %llu enqueued at %.3f\n", (unsigned long long)cj, host_ms());
+        CUDA_TRY(cudaEventRecord(sl.ev_c0, c->h2d_stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.pcm.p, (const uint8_t *)pcm + s0 * (u64)channels * (u64)cbytes, nb, cudaMemcpyHostToDevice, c->h2d_stream));
+        CUDA_TRY(cudaEventRecord(sl.ev_c1, c->h2d_stream));
+        h2d_issued[cj] = 1;
+        return FLACB_OK;
+    };
     for (u64 ci = 0; ci < n_chunks; ci++) {
         const int s = (int)(ci % FLACB_SLOTS);
         EncSlot &sl = c->slot[s];
@@ -913,22 +953,14 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
         if ((rc = retire(s))) return rc;
         if ((rc = finish_d2h(s))) return rc;
         if (status != FLACB_OK) break;
-        const u64 f0 = chunk_f0[ci];
-        const u64 nfr = chunk_f0[ci + 1] - f0;
-        const u64 s0 = f0 * (u64)block_size;
-        const u64 ns = (f0 + nfr == n_frames) ? n_sample_frames - s0 : nfr * (u64)block_size;
+        u64 f0, nfr, s0, ns;
+        chunk_span(ci, f0, nfr, s0, ns);
         EncodeArgs ca = a;
         ca.n_sample_frames = ns;
         ca.first_frame_number = first_frame_number + f0;
         const uint8_t *d_pcm = (const uint8_t *)pcm + s0 * (u64)channels * (u64)cbytes;
         if (host_in) {
-            const u64 nb = ns * (u64)channels * (u64)cbytes;
-            if ((rc = sl.pcm.ensure(nb))) return rc;
-            if (timeline) fprintf(stderr, "host: h2d of chunk %llu enqueued at %.3f\n", (unsigned long long)ci, host_ms());
-            /* the slot's previous chunk has been retired: nothing reads sl.pcm any more */
-            CUDA_TRY(cudaEventRecord(sl.ev_c0, c->h2d_stream));
-            CUDA_TRY(cudaMemcpyAsync(sl.pcm.p, d_pcm, nb, cudaMemcpyHostToDevice, c->h2d_stream));
-            CUDA_TRY(cudaEventRecord(sl.ev_c1, c->h2d_stream));
+            if ((rc = issue_h2d(ci))) return rc; /* unless it went out an iteration ago */
             CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_c1, 0));
             d_pcm = (const uint8_t *)sl.pcm.p;
         }
@@ -943,6 +975,7 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
         pend[s].f0 = f0;
         pend[s].nfr = nfr;
         pend[s].active = true;
+        if ((rc = issue_h2d(ci + 1))) return rc;
         /* Start the output copy of the chunk `ahead` behind this one now (it needs the chunk's
          * size on the host, hence a wait for its kernels) instead of when its slot is needed
          * again: by then the copy is done, and while the host waits here the copy engine and
@@ -956,6 +989,7 @@ static int encode_pcm_impl(flacb_ctx *c, const void *pcm, uint64_t n_sample_fram
     }
     for (int s = 0; s < FLACB_SLOTS; s++)
         if ((rc = finish_d2h(s))) return rc;
+    if (host_in && status != FLACB_OK) CUDA_TRY(cudaStreamSynchronize(c->h2d_stream)); /* a copy queued ahead still reads the caller's buffer */
     if (info && status != FLACB_E_CUDA) {
         CUDA_TRY(cudaMemcpyAsync(info, d_info, n_frames * (u64)channels * sizeof(flacb_subframe_info), cudaMemcpyDeviceToHost,
                                  c->slot[0].stream));
