@@ -357,18 +357,21 @@ def pcie_ceiling(world: int, local_rank: int, mb: int = 128, iters: int = 10) ->
             f()
         if world > 1:
             dist.all_reduce(sync_t)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            for f in fns:
-                f()
-        torch.cuda.synchronize()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out[name] = world * nbytes * iters / float(t.item()) / 1e9
+        best = 0.0
+        for _ in range(3):  # a ceiling: the best of three rounds (a round now and then runs at two thirds of the rate)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                for f in fns:
+                    f()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = max(best, world * nbytes * iters / float(t.item()) / 1e9)
+        out[name] = best
     return {"h2d_GBps": out["h2d"], "d2h_GBps": out["d2h"], "duplex_GBps": out["duplex"], "n_gpus": world,
-            "how": f"{mb} MiB pinned copies, every rank at the same time, max over ranks; aggregate over the ranks"}
+            "how": f"{mb} MiB pinned copies, every rank at the same time, max over ranks; aggregate over the ranks; best of three rounds"}
 
 
 def c4_strong(ctx, N, rank: int, world: int, local_rank: int, barrier, steps: int = 2) -> dict:
